@@ -1,0 +1,129 @@
+/* libprogen_b200.so — C ABI of the B200-native ProGen hot path.
+ *
+ * Drop-in boundary: the reference exposes `ProGen(**kwargs) -> .init / .apply`
+ * (lucidrains/progen progen_transformer/progen.py:235-243) and everything below that call is executed by XLA.
+ * This library replaces that device path.  Each entry point names the reference lines whose arithmetic it owns.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative PROGEN_ERR_* code; `progen_last_error()` (thread-local) has
+ *    the text.  Nothing allocates: the caller owns every buffer and workspace.  All work is asynchronous on `stream`
+ *    (a cudaStream_t passed as void*), no internal synchronisation, no global mutable state except a cache of TMA
+ *    descriptors keyed by (pointer, shape).
+ *  - tokens are rows: activations are row-major [T = B * seq_len, features]; `ld*` are element strides.
+ *  - dtype codes: PROGEN_F32 = 0, PROGEN_BF16 = 1.  The residual stream and all parameter gradients are fp32.
+ *  - sm_100a only (`progen_device_check`); there is no CPU or other-architecture fallback.
+ */
+#ifndef PROGEN_B200_H
+#define PROGEN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PROGEN_F32 0
+#define PROGEN_BF16 1
+
+#define PROGEN_BACKEND_SIMT 0     /* fp32-exact CUDA-core GEMM (mixed_precision=False path, progen.py:235) */
+#define PROGEN_BACKEND_TCGEN05 1  /* TMA + tcgen05.mma + TMEM GEMM, bf16 operands / fp32 accumulate */
+
+/* GEMM epilogues (fused with the matmul the reference line performs) */
+#define PROGEN_EPI_STORE 0     /* out = acc (+bias)                      progen.py:219-222 (logits), 185 (SGU proj)   */
+#define PROGEN_EPI_ROTARY 1    /* out = rotary(acc)                      progen.py:83-87 (to_qkv, rotary on q,k,v)    */
+#define PROGEN_EPI_RESIDUAL 2  /* out(f32) = (aux|out)(f32) + acc + bias   progen.py:103+230, 148+231                    */
+#define PROGEN_EPI_GLU 3       /* out2 = pre-act, out = val*gelu(gate)   progen.py:137-141                             */
+#define PROGEN_EPI_GELU 4      /* out2 = pre-act, out = gelu(pre)        progen.py:137,143                             */
+#define PROGEN_EPI_GLU_BWD 5   /* out = d(pre-act) from acc = d(GLU out) (backward of 3)                               */
+#define PROGEN_EPI_GELU_BWD 6  /* out = acc * gelu'(pre-act)             (backward of 4)                               */
+#define PROGEN_EPI_ACCUM 7     /* out(f32) += acc  (weight gradients; optional tril mask for SGU spatial_weights)     */
+
+const char* progen_version(void);
+const char* progen_last_error(void);
+int progen_device_check(void);
+
+/* D[M,N] (+)= A[M,K] * B[N,K]^T.  Operand X(m,k): K-major -> X[m*ld + k]; MN-major -> X[k*ld + m].
+ * Replaces every jnp matmul/einsum of the path: hk.Linear (progen.py:70-71,125-126,164,221), the SGU spatial
+ * einsum 'n d, m n -> m d' (progen.py:181; causal=1 skips the masked upper-triangular K tiles), and their
+ * transposes in the backward pass (jax.value_and_grad, utils.py:72). */
+typedef struct progen_gemm_t {
+  int32_t M, N, K;
+  int32_t a_mn_major, b_mn_major;
+  int32_t batch;         /* independent problems (grid z), >= 1 */
+  int32_t batch_reduce;  /* 1: all batches accumulate into the same output (needs EPI_ACCUM + atomic) */
+  int32_t causal;        /* 0 none, 1 lower (k < m0+128 only), 2 upper (k >= m0 only) */
+  int32_t split_k;       /* >= 1; > 1 needs EPI_ACCUM + atomic */
+  int32_t in_dtype, out_dtype, epi_kind, backend;
+  int32_t seq_len, dim_head;          /* EPI_ROTARY */
+  int32_t atomic, tril, tril_rows;    /* EPI_ACCUM */
+  int64_t lda, ldb;
+  int64_t a_batch_rows, b_batch_rows, d_batch_rows;   /* stored rows to skip per batch (0 = operand shared) */
+  int64_t ldo, ldo2, ldaux;
+  const void* A;
+  const void* B;
+  void* out;
+  void* out2;
+  const float* bias;
+  const void* aux;
+  const float* rot_sin;   /* [seq_len, dim_head/2], fixed_pos_embedding progen.py:24-28 */
+  const float* rot_cos;
+} progen_gemm_t;
+
+int progen_gemm(const progen_gemm_t* desc, void* stream);
+
+/* hk.Embed row gather — progen.py:207,226.  x is the fp32 residual stream [T, d]. */
+int progen_embed_fwd(const int* tokens, const float* table, float* x, long long T, int d, int V, void* stream);
+/* gradient of the gather: dtable[v,:] += sum_{t: tokens[t]==v} dx[t,:] */
+int progen_embed_bwd(const int* tokens, const float* dx, float* dtable, long long T, int d, int V, void* stream);
+
+/* y = shift_tokens(LayerNorm(x) * scale) — progen.py:22,43-46,74-77,132-135 (shift=1) and 170, 220 (shift=0).
+ * Saves mean / rstd per row for the backward pass. */
+int progen_ln_shift_fwd(const void* x, long long ldx, int x_dtype, const float* scale, void* y, long long ldy, int y_dtype,
+                        float* mean, float* rstd, long long T, int d, int seq_len, int shift, void* stream);
+/* backward of the above; residual=1 accumulates into the fp32 residual gradient `dres` [T,d] and mirrors it to `dout`. */
+int progen_ln_shift_bwd(const void* dy, long long lddy, int act_dtype, const void* x, long long ldx, int x_dtype,
+                        const float* scale, const float* mean, const float* rstd, float* dres, void* dout, long long ldo,
+                        float* dscale, long long T, int d, int seq_len, int shift, int residual, void* stream);
+
+/* out[c] += sum_t in[t,c] — bias gradients of every hk.Linear */
+int progen_colsum(const void* in, long long ld, int dtype, float* out, long long T, int N, void* stream);
+
+/* cross_entropy + masked_mean + batch mean — utils.py:42-59,76 (pad-as-EOS mask, Q8); fused forward + d(logits).
+ * *loss must be zeroed by the caller; inv_batch = 1/global_batch (DDP: a sum over ranks yields the global mean). */
+int progen_ce_fwd_bwd(const void* logits, int dtype, const int* labels, float* weights, float* loss, void* dlogits,
+                      int dlogits_dtype, int B, int n, int V, float inv_batch, void* stream);
+
+/* backward of apply_rotary_pos_emb (progen.py:36-41) on the [T, ncols] q|k|v gradient, in place */
+int progen_rotary_bwd(void* dqkv, long long ld, int dtype, const float* sin_t, const float* cos_t, long long T, int ncols,
+                      int seq_len, int dim_head, void* stream);
+
+/* sliding-window attention with one look-back window — progen.py:88-102 (q,k,v already rotated, [T, 3*heads*dim_head]).
+ * `_simt`: fp32-exact CUDA-core kernels.  lse / delta: [T, heads] fp32. */
+int progen_local_attn_fwd_simt(const void* qkv, void* out, float* lse, int dtype, int B, int seq_len, int window, int heads,
+                               int dim_head, void* stream);
+int progen_local_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                               float* delta, int dtype, int B, int seq_len, int window, int heads, int dim_head,
+                               void* stream);
+
+/* SGU gating — progen.py:182-184: out = xs * (Gp + spatial_biases[m]) and its backward (dxs, dGp, dbias) */
+int progen_sgu_gate_fwd(const void* xs, long long ldx, const void* gp, long long ldg, const float* bias, void* out,
+                        long long ldo, int dtype, long long T, int C, int seq_len, void* stream);
+int progen_sgu_gate_bwd(const void* ds, long long ldds, const void* xs, long long ldx, const void* gp, long long ldg,
+                        const float* bias, void* dxs, long long lddx, void* dgp, long long lddg, float* dbias, int dtype,
+                        long long T, int C, int seq_len, void* stream);
+/* da *= gelu'(u) (tanh-approximate GELU, jax.nn.gelu default — progen.py:143) */
+int progen_gelu_bwd(void* da, const void* u, int dtype, long long numel, void* stream);
+int progen_cast_f32(const float* in, void* out, int out_dtype, long long numel, void* stream);
+/* out = tril(spatial_weights) in the act dtype — the mask of progen.py:178-179 applied once per parameter update */
+int progen_tril_cast(const float* w, void* out, int out_dtype, int n, void* stream);
+
+/* optimizer: optax.chain(clip_by_global_norm, adamw(mask = ndim > 1), apply_every(k)) — train.py:115-121,189-190 */
+int progen_optim_workspace_floats(void);
+int progen_grad_sqnorm(const float* g, long long n, float* workspace, float* out_sqnorm, void* stream);
+int progen_adamw_step(float* p, void* p_lp, const float* g, float* m, float* v, float* acc, long long n, long long n_decay,
+                      const float* gnorm_sq, float lr, float b1, float b2, float eps, float wd, float max_norm,
+                      long long step, int emit, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROGEN_B200_H */

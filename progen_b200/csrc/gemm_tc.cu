@@ -1,0 +1,470 @@
+// tcgen05 GEMM for sm_100a: D[M,N] (+)= A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulation in TMEM.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one thread: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction)
+//   warp 2      : TMEM allocator (2 accumulator stages of BN fp32 columns)
+//   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//
+// Persistent: one CTA per SM loops over output tiles; the two TMEM accumulator stages let the epilogue of
+// tile i overlap the mainloop of tile i+1.  Operands may be K-major or MN-major (wgrad reads the activations
+// and the output gradient with the token dimension as K, i.e. MN-major) — both go through the same 128B-swizzled
+// shared-memory layout, only the UMMA descriptors differ.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include "gemm.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BN> struct TileCfg {
+  static constexpr int A_BYTES = BM * BK * 2;           // 16 KiB
+  static constexpr int B_BYTES = BN * BK * 2;           // 16 / 32 KiB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;   // 6 (BN=128) / 4 (BN=256)
+  static constexpr int TMEM_COLS = 2 * BN;              // 256 / 512
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();   // a protocol bug must fail loudly instead of hanging the GPU
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------- UMMA descriptors
+// Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
+//   K-major  tile (rows x 64 bf16, 128 B per row): 8-row groups 1024 B apart -> SBO = 1024; LBO unused (1).
+//   MN-major tile (64-element MN chunks of [64 k-rows x 128 B], chunks 8192 B apart): LBO = 8192 (next MN chunk),
+//            SBO = 1024 (next 8 k-rows).
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(MN_MAJOR ? (8192 >> 4) : 1) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// advancing one UMMA_K (16 elements) inside a stage: K-major +32 B; MN-major +16 k-rows * 128 B = 2048 B
+template <bool MN_MAJOR> __device__ __forceinline__ uint32_t desc_k_step() { return MN_MAJOR ? (2048 >> 4) : (32 >> 4); }
+
+// Instruction descriptor (InstrDescriptor): c_format F32 (1) [4,6), a/b_format BF16 (1) [7,10)/[10,13),
+// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+template <int BN, bool A_MN, bool B_MN> __device__ __forceinline__ uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct GemmDev {
+  int M, N, K;
+  int batch, batch_reduce;
+  int a_batch_rows, b_batch_rows;
+  long long d_batch_rows;
+  int causal, split_k;
+  EpiArgs epi;
+};
+
+struct TileInfo {
+  int z, ks, m0, n0, kb_begin, kb_end;
+};
+
+template <int BN>
+__device__ __forceinline__ bool decode_tile(const GemmDev& g, int t, TileInfo& ti) {
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int per_z = g.split_k * m_tiles * n_tiles;
+  if (t >= per_z * g.batch) return false;
+  ti.z = t / per_z;
+  int r = t - ti.z * per_z;
+  ti.ks = r / (m_tiles * n_tiles);
+  r -= ti.ks * (m_tiles * n_tiles);
+  ti.m0 = (r / n_tiles) * BM;
+  ti.n0 = (r % n_tiles) * BN;
+  const int kb_total = (g.K + BK - 1) / BK;
+  int b = 0, e = kb_total;
+  if (g.causal == 1) e = min(kb_total, (ti.m0 + BM + BK - 1) / BK);
+  if (g.causal == 2) b = min(kb_total, ti.m0 / BK);
+  if (g.split_k > 1) {
+    const int per = (kb_total + g.split_k - 1) / g.split_k;
+    b = ti.ks * per;
+    e = min(kb_total, b + per);
+  }
+  ti.kb_begin = b;
+  ti.kb_end = e;
+  return true;
+}
+
+template <int BN, bool A_MN, bool B_MN, int KIND, typename TO>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);            // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      TileInfo ti;
+      for (int t = blockIdx.x; decode_tile<BN>(g, t, ti); t += gridDim.x) {
+        const int a_row0 = ti.z * g.a_batch_rows;
+        const int b_row0 = ti.z * g.b_batch_rows;
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tma_a, full_bar(stage), k0, a_row0 + ti.m0);                 // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)                                              // boxes {64 m, 64 k}
+              tma_load_2d(sa + i * 8192, &tma_a, full_bar(stage), ti.m0 + 64 * i, a_row0 + k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tma_b, full_bar(stage), k0, b_row0 + ti.n0);                 // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)                                              // boxes {64 n, 64 k}
+              tma_load_2d(sb + i * 8192, &tma_b, full_bar(stage), ti.n0 + 64 * i, b_row0 + k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      TileInfo ti;
+      for (int t = blockIdx.x; decode_tile<BN>(g, t, ti); t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);      // epilogue has drained this accumulator stage
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc<A_MN>(sa);
+          const uint64_t bdesc = make_smem_desc<B_MN>(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * desc_k_step<A_MN>()), bdesc + (uint64_t)(k * desc_k_step<B_MN>()),
+                      idesc, (kb > ti.kb_begin || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(stage));             // smem slot is free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(tfull_bar(acc));                 // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (warps 4..7 <-> TMEM lanes 0..127)
+    const int q = warp & 3;
+    const int r_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    TileInfo ti;
+    for (int t = blockIdx.x; decode_tile<BN>(g, t, ti); t += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int m = ti.m0 + r_in_tile;
+      const long long row = (g.batch_reduce ? 0 : (long long)ti.z * g.d_batch_rows) + m;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const bool has_k = ti.kb_end > ti.kb_begin;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = ti.n0 + c * 32;
+        if (col >= g.N) break;                          // warp-uniform
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);                   // .sync.aligned: executed by the whole warp
+        if (!has_k) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (m < g.M) epi_apply<KIND, TO, 32>(g.epi, row, col, v);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; uint64_t inner, outer, stride; uint32_t box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && stride == o.stride && box_inner == o.box_inner &&
+           box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.stride); mix(k.box_inner); mix(k.box_outer);
+    return h;
+  }
+};
+
+// 2D bf16 tensor map: inner (contiguous) dimension first; 128B swizzle; OOB reads return zeros.
+int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_elems, uint32_t box_inner,
+                   uint32_t box_outer, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{ptr, inner, outer, row_stride_elems, box_inner, box_outer};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return PROGEN_OK; }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { progen_set_error("cuTensorMapEncodeTiled driver entry point not found"); return PROGEN_ERR_DEVICE; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    progen_set_error("cuTensorMapEncodeTiled failed (CUresult %d) ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r,
+                     ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_elems,
+                     box_inner, box_outer);
+    return PROGEN_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return PROGEN_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int KIND, typename TO>
+int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& gd, int tiles, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, KIND, TO>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int grid = tiles < pg_num_sms() ? tiles : pg_num_sms();
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, gd);
+  PG_LAUNCH_CHECK();
+  return PROGEN_OK;
+}
+
+template <bool A_MN, bool B_MN, int KIND, typename TO>
+int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& gd, int tiles, cudaStream_t s) {
+  if (bn == 256) return launch_inst<256, A_MN, B_MN, KIND, TO>(ta, tb, gd, tiles, s);
+  return launch_inst<128, A_MN, B_MN, KIND, TO>(ta, tb, gd, tiles, s);
+}
+
+}  // namespace
+
+int gemm_tc_launch(const GemmArgs& a, cudaStream_t stream) {
+  PG_CHECK_ARG(a.in_dtype == PG_BF16);
+  PG_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0 && a.batch >= 1 && a.split_k >= 1);
+  PG_CHECK_ARG(a.N % 32 == 0);
+  PG_CHECK_ARG(a.K % BK == 0);                       // TMA would zero-fill a K tail, but batched operands must not bleed
+  PG_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0);    // 16-byte global strides for TMA
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
+  PG_CHECK_ARG(!(a.split_k > 1 && a.causal));
+  PG_CHECK_ARG(!(a.split_k > 1 || a.batch_reduce) || (a.epi_kind == EPI_ACCUM && a.epi.atomic));
+  if (a.batch > 1 && a.a_batch_rows > 0 && !a.a_mn_major) PG_CHECK_ARG(a.M % BM == 0 || a.batch_reduce || true);
+
+  const int bn = (a.N >= 256 && a.N % 256 == 0) ? 256 : 128;
+  // stored 2D extents of each operand
+  const uint64_t a_rows = (a.batch > 1 && a.a_batch_rows > 0) ? (uint64_t)a.a_batch_rows * a.batch
+                                                              : (uint64_t)(a.a_mn_major ? a.K : a.M);
+  const uint64_t b_rows = (a.batch > 1 && a.b_batch_rows > 0) ? (uint64_t)a.b_batch_rows * a.batch
+                                                              : (uint64_t)(a.b_mn_major ? a.K : a.N);
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a.a_mn_major) rc = get_tensor_map(a.A, a.K, a_rows, a.lda, BK, BM, &ta);
+  else               rc = get_tensor_map(a.A, a.M, a_rows, a.lda, 64, BK, &ta);
+  if (rc) return rc;
+  if (!a.b_mn_major) rc = get_tensor_map(a.B, a.K, b_rows, a.ldb, BK, bn, &tb);
+  else               rc = get_tensor_map(a.B, a.N, b_rows, a.ldb, 64, BK, &tb);
+  if (rc) return rc;
+
+  GemmDev gd;
+  gd.M = a.M; gd.N = a.N; gd.K = a.K;
+  gd.batch = a.batch; gd.batch_reduce = a.batch_reduce;
+  gd.a_batch_rows = (int)a.a_batch_rows; gd.b_batch_rows = (int)a.b_batch_rows; gd.d_batch_rows = a.d_batch_rows;
+  gd.causal = a.causal; gd.split_k = a.split_k;
+  gd.epi = a.epi;
+  const int tiles = a.batch * a.split_k * ((a.M + BM - 1) / BM) * ((a.N + bn - 1) / bn);
+
+  const int am = a.a_mn_major ? 1 : 0, bm = a.b_mn_major ? 1 : 0;
+  const bool obf = a.out_dtype == PG_BF16;
+#define TC_CASE(AM, BMJ, KIND, TO) return launch_bn<AM, BMJ, KIND, TO>(bn, ta, tb, gd, tiles, stream)
+  switch (a.epi_kind) {
+    case EPI_STORE:
+      if (!am && bm) { if (obf) TC_CASE(false, true, EPI_STORE, bf16); else TC_CASE(false, true, EPI_STORE, float); }
+      if (!am && !bm) { if (obf) TC_CASE(false, false, EPI_STORE, bf16); else TC_CASE(false, false, EPI_STORE, float); }
+      if (am && bm) { if (obf) TC_CASE(true, true, EPI_STORE, bf16); else TC_CASE(true, true, EPI_STORE, float); }
+      break;
+    case EPI_ROTARY:
+      if (!am && bm && obf) TC_CASE(false, true, EPI_ROTARY, bf16);
+      break;
+    case EPI_RESIDUAL:
+      if (!am && bm) TC_CASE(false, true, EPI_RESIDUAL, float);
+      break;
+    case EPI_GLU:
+      if (!am && bm && obf) TC_CASE(false, true, EPI_GLU, bf16);
+      break;
+    case EPI_GELU:
+      if (!am && bm && obf) TC_CASE(false, true, EPI_GELU, bf16);
+      break;
+    case EPI_GLU_BWD:
+      if (!am && !bm && obf) TC_CASE(false, false, EPI_GLU_BWD, bf16);
+      break;
+    case EPI_GELU_BWD:
+      if (!am && !bm && obf) TC_CASE(false, false, EPI_GELU_BWD, bf16);
+      break;
+    case EPI_ACCUM:
+      if (am && bm) TC_CASE(true, true, EPI_ACCUM, float);
+      if (!am && !bm) TC_CASE(false, false, EPI_ACCUM, float);
+      break;
+    default: break;
+  }
+#undef TC_CASE
+  progen_set_error("gemm_tc: unsupported combination epi=%d a_mn=%d b_mn=%d out=%d", a.epi_kind, am, bm, a.out_dtype);
+  return PROGEN_ERR_UNSUPPORTED;
+}
