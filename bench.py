@@ -1,0 +1,310 @@
+"""bench.py — tokens/sec of one ProGen training step (BASELINE.json configs[1]) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm: the oracle port timed on the host cores
+
+A "step" is one pass of the hot path over one synthetic batch: forward + loss + backward + (DDP gradient all-reduce) +
+clip/AdamW/apply_every, i.e. one iteration of the reference's inner loop (train.py:186-190).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    'cfg2': dict(kwargs=dict(num_tokens=256, dim=512, seq_len=1024, depth=12, heads=8, dim_head=64, window_size=256,
+                             global_mlp_depth=2, ff_glu=True), batch=64,
+                 name='ProGen dim=512 depth=12 heads=8 seq_len=1024 window=256 gmlp=2 bf16 - training step, synthetic batch=64/GPU (BASELINE configs[1])'),
+    'cfg3': dict(kwargs=dict(num_tokens=256, dim=1024, seq_len=2048, depth=24, heads=16, dim_head=64, window_size=512,
+                             global_mlp_depth=2, ff_glu=True), batch=8,
+                 name='ProGen dim=1024 depth=24 heads=16 seq_len=2048 window=512 gmlp=2 bf16 - training step (BASELINE configs[2])'),
+    'tiny': dict(kwargs=dict(num_tokens=256, dim=128, seq_len=128, depth=2, heads=2, dim_head=64, window_size=64,
+                             global_mlp_depth=1, ff_glu=True), batch=4, name='tiny smoke configuration (not a bench line)'),
+}
+
+
+def fwd_flops_per_token(kw):
+    """causal-algorithmic forward FLOPs per token (LN / softmax / GELU / rotary excluded)."""
+    d, n, w = kw['dim'], kw['seq_len'], kw['window_size']
+    I = kw['heads'] * kw['dim_head']
+    V = kw['num_tokens']
+    total = 2 * d * V
+    for i in range(kw['depth']):
+        attn = 6 * d * I + 2 * I * d + 4 * I * (w + (w + 1) / 2)
+        gmlp = (kw['depth'] - i) <= kw['global_mlp_depth']
+        ff = (20 * d * d + 2 * (n + 1) * d) if gmlp else (24 * d * d if kw['ff_glu'] else 16 * d * d)
+        total += attn + ff
+    return total
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(burst=j['bf16_tflops'], sustained=j.get('bf16_tflops_sustained', j['bf16_tflops']), hbm=j['hbm_gbs'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def synthetic_batches(count, B, n, seed):
+    """uniform-random [0,256) rows of n+1 tokens (BASELINE north_star), int32, pinned when a GPU is present"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        t = torch.from_numpy(rng.integers(0, 256, (B, n + 1)).astype(np.int32))
+        out.append(t.pin_memory() if torch.cuda.is_available() else t)
+    return out
+
+
+def cpu_port_tokens_per_sec(kw, steps, warmup, rows=2, seed=123):
+    """The reference's Jax path is not installable (no jax wheels, no network), so the timed CPU implementation is the
+    oracle's torch port of the same algorithm: fp32, all host cores through torch intra-op threads, fwd + bwd."""
+    from oracle import progen_ref as O
+    from oracle import progen_torch as T
+    cfg = O.make_config(**kw)
+    params = O.init_params(cfg, 0)
+    prm = T.to_torch(params, torch.float32, requires_grad=True)
+    rng = np.random.default_rng(seed)
+    n = cfg['seq_len']
+    times = []
+    for i in range(warmup + steps):
+        data = torch.as_tensor(rng.integers(0, 256, (rows, n + 1)).astype(np.int64))
+        t0 = time.perf_counter()
+        loss = T.batch_loss(prm, data, cfg)
+        loss.backward()
+        for d in prm.values():
+            for v in d.values():
+                v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return rows * n / sec, sec, rows
+
+
+def run_reference_arm(args, cfgd):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    kw = cfgd['kwargs']
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    tps, sec, rows = cpu_port_tokens_per_sec(kw, max(1, args.steps), max(1, args.warmup), rows=2)
+    sample = f'{rows} sequences x {kw["seq_len"]} tokens per step (fwd+bwd, fp32), {args.steps} timed steps'
+    line = dict(impl='reference', metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=0, steps=args.steps,
+                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', config=dict(workload=cfgd['name']),
+                cpu_baseline=dict(value=tps, unit='tokens/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=tps, unit='tokens/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note='reference Jax/Haiku is not installable here (no jax/jaxlib/haiku wheels, no network); this is the '
+                     'oracle torch port of the same algorithm on the host cores')
+    print(json.dumps(line), flush=True)
+
+
+def time_dominant_gemm(eng, iters=20):
+    """The dominant kernel: the tcgen05 GEMM on its largest single shape of this config (FF proj_in forward,
+    [T, d] x [d, 8d] with the GLU epilogue), timed alone with CUDA events on the launching stream."""
+    from progen_b200 import lib as L
+    from progen_b200.engine import P
+    i = next(j for j, k in enumerate(eng.kinds) if k == 'glu') if 'glu' in eng.kinds else None
+    if i is None:
+        return None
+    s = eng.lay[i]
+    f = P + f'ff{i}/~/'
+    hid, d, T = eng.hid, eng.d, eng.T
+
+    def launch():
+        eng.fwd_gemm(s['y2'], d, eng.W(f + 'linear', 'w'), 2 * hid, s['hact'], epi=L.EPI_GLU, ldo=hid, out2=s['u'], ldo2=2 * hid,
+                     bias=eng.Pf(f + 'linear', 'b'))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        launch()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    flops = 2.0 * T * d * 2 * hid
+    return dict(kernel='gemm_tc_kernel<256,K-major,MN-major,EPI_GLU> (FF proj_in fwd)', shape=[T, 2 * hid, d], ms=ms,
+                tflops=flops / ms / 1e9)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS))
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch override')
+    ap.add_argument('--fp32', action='store_true', help='fp32 engine (parity path) instead of bf16')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == 'b200' else args.warmup
+    cfgd = CONFIGS[args.config]
+    kw = cfgd['kwargs']
+    if args.impl == 'reference':
+        run_reference_arm(args, cfgd)
+        return
+
+    import torch.distributed as dist
+    from progen_b200 import ProGen, lib as L
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    L.require_device()
+    B = args.batch or cfgd['batch']
+    n = kw['seq_len']
+    model = ProGen(**kw, mixed_precision=not args.fp32)
+    params = model.init(1234)                      # same seed on every rank: identical replicas
+    tr = model.trainer(params)                     # reference optimizer chain, grad_accum_every=4
+    eng = model.engine
+    total = args.warmup + args.steps
+    batches = synthetic_batches(total, B, n, 42 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg: inputs already in HBM when the timed region starts
+    dev_batches = [b.cuda() for b in batches]
+    for i in range(args.warmup):
+        eng.ensure_batch(B)
+        eng.tok.copy_(dev_batches[i][:, :-1].reshape(-1)); eng.labels.copy_(dev_batches[i][:, 1:].reshape(-1))
+        tr.step_resident(global_batch=B * world)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = L.load().progen_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, total):
+        eng.tok.copy_(dev_batches[i][:, :-1].reshape(-1)); eng.labels.copy_(dev_batches[i][:, 1:].reshape(-1))
+        tr.step_resident(global_batch=B * world)
+    e1.record()
+    barrier()
+    launches = L.load().progen_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(eng.loss.item())
+
+    # ---------------- end-to-end leg: public API with HOST (pinned) buffers, H2D + loss D2H inside the timed region
+    for i in range(min(2, args.warmup)):
+        float(tr.step(batches[i]).item())
+    barrier()
+    e0.record()
+    for i in range(args.warmup, total):
+        float(tr.step(batches[i]).item())
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2.item())
+
+    tokens_per_step = B * n * world
+    tps = tokens_per_step * args.steps / (ms_total / 1e3)
+    tps_e2e = tokens_per_step * args.steps / (ms_e2e / 1e3)
+    if rank == 0:
+        peaks = measured_peaks()
+        train_flops = 3.0 * fwd_flops_per_token(kw)
+        achieved = tps * train_flops / 1e12 / world
+        dom = time_dominant_gemm(eng) if not args.fp32 else None
+        roofline = dict(bound='tensor', achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s', frac=achieved / peaks['sustained'],
+                        traffic=None, peak_source=peaks['source'] + ', sustained figure (kernel timed inside a long step)',
+                        definition='whole step: tokens/s x 3 x F_fwd (SURVEY 8d, %.2f MFLOP/token train) per GPU' % (train_flops / 1e6))
+        if dom:
+            roofline['dominant_kernel'] = dict(dom, peak=peaks['burst'], frac=dom['tflops'] / peaks['burst'],
+                                               peak_source=peaks['source'] + ', burst figure (kernel timed alone)')
+        line = dict(metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f32' if args.fp32 else 'bf16', data='synthetic',
+                    config=dict(workload=cfgd['name'], global_batch=B * world, seq_len=n, parallelism=f'dp{world}',
+                                l2='activations (~%.1f GB/step) far exceed the 126 MB L2; no explicit flush' % (eng_bytes(eng) / 1e9),
+                                optimizer='clip_by_global_norm(0.5)+adamw(2e-4,wd=1e-3,mask)+apply_every(4), every step'),
+                    e2e=dict(value=tps_e2e, unit='tokens/s', h2d_bytes_per_step=B * (n + 1) * 4, d2h_bytes_per_step=4,
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, final_loss=final_loss)
+        if not args.no_cpu_baseline and world == 1:
+            cores = len(os.sched_getaffinity(0))
+            torch.set_num_threads(cores)
+            v, sec, rows = cpu_port_tokens_per_sec(kw, steps=2, warmup=1, rows=2)
+            line['cpu_baseline'] = dict(value=v, unit='tokens/s', cores=cores, kind='port',
+                                        sample=f'{rows} sequences x {n} tokens, fwd+bwd fp32, 2 timed steps ({sec:.1f} s each)')
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def eng_bytes(eng):
+    tot = 0
+    for s in eng.lay:
+        for v in s.values():
+            tot += v.numel() * v.element_size()
+    for x in eng.X:
+        tot += x.numel() * 4
+    return tot
+
+
+if __name__ == '__main__':
+    main()

@@ -40,6 +40,8 @@ extern "C" {
 const char* progen_version(void);
 const char* progen_last_error(void);
 int progen_device_check(void);
+/* number of kernels this library has launched in this process (bench.py reports the per-run delta) */
+long long progen_launch_count(void);
 
 /* D[M,N] (+)= A[M,K] * B[N,K]^T.  Operand X(m,k): K-major -> X[m*ld + k]; MN-major -> X[k*ld + m].
  * Replaces every jnp matmul/einsum of the path: hk.Linear (progen.py:70-71,125-126,164,221), the SGU spatial

@@ -4,6 +4,7 @@
 #include "../../include/progen_b200.h"
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_progen_launches = 0;
 
 void progen_set_error(const char* fmt, ...) {
   va_list ap;
@@ -17,6 +18,8 @@ extern "C" {
 const char* progen_version(void) { return "progen_b200 0.1.0 (sm_100a; tcgen05/TMA GEMM, CUDA " CUDA_VERSION_STR ")"; }
 
 const char* progen_last_error(void) { return g_err; }
+
+long long progen_launch_count(void) { return (long long)g_progen_launches; }
 
 // north_star: no CPU fallback, sm_100 only.  Returns 0 iff the current device can run every kernel in this library.
 int progen_device_check(void) {

@@ -35,7 +35,13 @@ void progen_set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
-#define PG_LAUNCH_CHECK() PG_CUDA(cudaPeekAtLastError())
+// every kernel launch is followed by PG_LAUNCH_CHECK(): it also feeds progen_launch_count() (bench.py's gpu_launches)
+extern unsigned long long g_progen_launches;
+#define PG_LAUNCH_CHECK()                 \
+  do {                                    \
+    ++g_progen_launches;                  \
+    PG_CUDA(cudaPeekAtLastError());       \
+  } while (0)
 
 // dtype enum shared with the Python host layer (progen_b200/lib.py)
 enum : int { PG_F32 = 0, PG_BF16 = 1 };

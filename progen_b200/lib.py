@@ -44,6 +44,7 @@ PROTOTYPES = {
     'progen_version': [],
     'progen_last_error': [],
     'progen_device_check': [],
+    'progen_launch_count': [],
     'progen_gemm': [C.POINTER(GemmDesc), _P],
     'progen_embed_fwd': [_P, _P, _P, _LL, _I, _I, _P],
     'progen_embed_bwd': [_P, _P, _P, _LL, _I, _I, _P],
@@ -63,7 +64,7 @@ PROTOTYPES = {
     'progen_grad_sqnorm': [_P, _LL, _P, _P, _P],
     'progen_adamw_step': [_P, _P, _P, _P, _P, _P, _LL, _LL, _P, _F, _F, _F, _F, _F, _F, _LL, _I, _P],
 }
-_RESTYPES = {'progen_version': C.c_char_p, 'progen_last_error': C.c_char_p}
+_RESTYPES = {'progen_version': C.c_char_p, 'progen_last_error': C.c_char_p, 'progen_launch_count': C.c_longlong}
 
 
 def load():

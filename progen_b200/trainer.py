@@ -1,0 +1,94 @@
+"""Device-resident training state for the train.py loop: parameters, gradients, Adam moments and the apply_every
+accumulator live in flat fp32 buffers; one `step(data)` is one iteration of the reference's inner loop
+(train.py:186-190): loss+grads, optim.update, apply_updates."""
+import numpy as np
+import torch
+
+from . import lib as L
+from . import parallel as PAR
+
+
+class Trainer:
+    def __init__(self, model, params, learning_rate=2e-4, weight_decay=1e-3, max_grad_norm=0.5, grad_accum_every=4,
+                 b1=0.9, b2=0.999, eps=1e-8, optim_state=None, data_parallel=True):
+        self.model = model
+        self.eng = model.engine
+        self.eng.load_params(params)
+        model._loaded = None
+        self.lr, self.wd, self.max_norm, self.every = learning_rate, weight_decay, max_grad_norm, grad_accum_every
+        self.b1, self.b2, self.eps = b1, b2, eps
+        n = self.eng.n_params_padded
+        z = lambda: torch.zeros(n, device=self.eng.dev, dtype=torch.float32)
+        self.m, self.v, self.acc = z(), z(), z()
+        self.count = 0
+        self.ws = torch.empty(L.load().progen_optim_workspace_floats(), device=self.eng.dev)
+        self.gnorm_sq = torch.zeros(1, device=self.eng.dev)
+        self.rank, self.world = PAR.world() if data_parallel else (0, 1)
+        if optim_state is not None:
+            self.load_optim_state(optim_state)
+
+    # ---- one micro-step of train.py:186-190
+    def step(self, data, sync_loss=False):
+        """data: this rank's rows, (b, n+1) integers.  Returns the device scalar loss (global mean when sync_loss)."""
+        gb = data.shape[0] * self.world if self.world > 1 else data.shape[0]
+        self.eng.loss_and_grad(data, global_batch=gb)
+        return self._update(sync_loss)
+
+    def step_resident(self, global_batch=None, sync_loss=False):
+        """same, on tokens/labels already copied into engine.tok / engine.labels (bench: inputs resident in HBM)"""
+        self.eng.step_device(global_batch or self.eng.B * self.world)
+        return self._update(sync_loss)
+
+    def _update(self, sync_loss):
+        eng, lib, st = self.eng, L.load(), L.stream()
+        if self.world > 1:
+            PAR.allreduce_sum_(eng.grads)
+            if sync_loss:
+                PAR.allreduce_scalar_(eng.loss)
+        self.count += 1
+        emit = int(self.count % self.every == 0)
+        L.check(lib.progen_grad_sqnorm(eng.grads.data_ptr(), eng.n_params_padded, self.ws.data_ptr(), self.gnorm_sq.data_ptr(), st),
+                'grad_sqnorm')
+        L.check(lib.progen_adamw_step(eng.params.data_ptr(), eng.params_lp.data_ptr() if eng.mp else 0, eng.grads.data_ptr(),
+                                      self.m.data_ptr(), self.v.data_ptr(), self.acc.data_ptr(), eng.n_params_padded, eng.n_decay,
+                                      self.gnorm_sq.data_ptr(), self.lr, self.b1, self.b2, self.eps, self.wd, self.max_norm,
+                                      self.count, emit, st), 'adamw_step')
+        if emit:
+            eng.refresh_masked_copies()
+        return eng.loss
+
+    def evaluate(self, data):
+        """validation loss (train.py:207-211): forward + loss only"""
+        eng = self.eng
+        d = torch.as_tensor(np.asarray(data).astype(np.int32) if not isinstance(data, torch.Tensor) else data)
+        eng.ensure_batch(d.shape[0])
+        dd = d.to(device=eng.dev, dtype=torch.int32)
+        eng.tok.copy_(dd[:, :-1].reshape(-1))
+        eng.labels.copy_(dd[:, 1:].reshape(-1))
+        eng._forward_device()
+        eng.loss.zero_()
+        L.check(L.load().progen_ce_fwd_bwd(eng.logits.data_ptr(), L.F32, eng.labels.data_ptr(), eng.ce_w.data_ptr(), eng.loss.data_ptr(),
+                                           0, eng.act_dt, eng.B, eng.n, eng.V, 1.0 / d.shape[0], L.stream()), 'ce_fwd')
+        return eng.loss
+
+    # ---- checkpoint interchange (haiku-shaped trees, train.py:196-202)
+    def params(self):
+        return self.eng.export_params()
+
+    def optim_state(self):
+        e = self.eng
+        return dict(count=self.count, mu=e.export_tree(self.m), nu=e.export_tree(self.v), acc=e.export_tree(self.acc),
+                    every=self.every)
+
+    def load_optim_state(self, st):
+        e = self.eng
+        self.count = int(st['count'])
+        for buf, tree in ((self.m, st['mu']), (self.v, st['nu']), (self.acc, st['acc'])):
+            host = np.zeros(e.n_params_padded, np.float32)
+            for s in e.specs:
+                a = np.asarray(tree[s.module][s.name], np.float32)
+                if s.interleave:
+                    from .engine import _interleave
+                    a = _interleave(a)
+                host[s.offset:s.offset + s.size] = a.ravel()
+            buf.copy_(torch.from_numpy(host))
