@@ -139,8 +139,10 @@ def run_reference_arm(args, cfgd):
     kw = cfgd['kwargs']
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    tps, sec, rows = cpu_port_tokens_per_sec(kw, max(1, args.steps), max(1, args.warmup), rows=2)
-    sample = f'{rows} sequences x {kw["seq_len"]} tokens per step (fwd+bwd, fp32), {args.steps} timed steps'
+    # bounded sample: one sequence per step, at most 3 timed steps + 1 warm-up (~40 s each on the box host cores)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    tps, sec, rows = cpu_port_tokens_per_sec(kw, steps, warmup, rows=1)
+    sample = f"{rows} sequence x {kw['seq_len']} tokens per step (fwd+bwd, fp32), {steps} timed steps (of --steps {args.steps})"
     line = dict(impl='reference', metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=0, steps=args.steps,
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', config=dict(workload=cfgd['name']),
@@ -287,9 +289,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0))
             torch.set_num_threads(cores)
-            v, sec, rows = cpu_port_tokens_per_sec(kw, steps=2, warmup=1, rows=2)
+            v, sec, rows = cpu_port_tokens_per_sec(kw, steps=1, warmup=1, rows=1)
             line['cpu_baseline'] = dict(value=v, unit='tokens/s', cores=cores, kind='port',
-                                        sample=f'{rows} sequences x {n} tokens, fwd+bwd fp32, 2 timed steps ({sec:.1f} s each)')
+                                        sample=f'{rows} sequences x {n} tokens, fwd+bwd fp32, 1 timed step ({sec:.1f} s)')
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

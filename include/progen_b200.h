@@ -106,6 +106,12 @@ int progen_local_attn_bwd_simt(const void* qkv, const void* out, const void* dou
                                float* delta, int dtype, int B, int seq_len, int window, int heads, int dim_head,
                                void* stream);
 
+/* tensor-core version (bf16, dim_head 64, window % 64 == 0): flash-style, scores stay on chip; same buffers as above */
+int progen_local_attn_fwd(const void* qkv, void* out, float* lse, int B, int seq_len, int window, int heads, int dim_head,
+                          void* stream);
+int progen_local_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                          int B, int seq_len, int window, int heads, int dim_head, void* stream);
+
 /* SGU gating — progen.py:182-184: out = xs * (Gp + spatial_biases[m]) and its backward (dxs, dGp, dbias) */
 int progen_sgu_gate_fwd(const void* xs, long long ldx, const void* gp, long long ldg, const float* bias, void* out,
                         long long ldo, int dtype, long long T, int C, int seq_len, void* stream);

@@ -94,6 +94,8 @@ class Engine:
         self.act_dt = L.BF16 if self.mp else L.F32
         self.backend = L.BACKEND_TC if self.mp else L.BACKEND_SIMT
         self.kinds = layer_kinds(cfg['depth'], cfg['global_mlp_depth'], cfg['ff_glu'])
+        # tensor-core attention kernel needs bf16, dim_head 64 and 64-aligned windows; other shapes use the CUDA-core kernel
+        self.attn_tc = self.mp and cfg['dim_head'] == 64 and cfg['window_size'] % 64 == 0
         d, n, w = cfg['dim'], cfg['seq_len'], cfg['window_size']
         self.d, self.n, self.w, self.V = d, n, w, cfg['num_tokens']
         self.h, self.dh = cfg['heads'], cfg['dim_head']
@@ -322,10 +324,19 @@ class Engine:
         self.fwd_gemm(self.yf, d, self.W(P + 'linear', 'w'), self.V, self.logits, bias=self.Pf(P + 'linear', 'b'), out_dtype=L.F32)
 
     def attn_fwd(self, qkv, out, lse):
+        if self.attn_tc:
+            L.check(self.lib.progen_local_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), self.B, self.n, self.w, self.h,
+                                                   self.dh, L.stream()), 'local_attn_fwd')
+            return
         L.check(self.lib.progen_local_attn_fwd_simt(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), self.act_dt, self.B, self.n,
                                                     self.w, self.h, self.dh, L.stream()), 'local_attn_fwd')
 
     def attn_bwd(self, qkv, out, dout, lse, dqkv):
+        if self.attn_tc:
+            L.check(self.lib.progen_local_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                                   self.delta.data_ptr(), self.B, self.n, self.w, self.h, self.dh, L.stream()),
+                    'local_attn_bwd')
+            return
         L.check(self.lib.progen_local_attn_bwd_simt(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                                     self.delta.data_ptr(), self.act_dt, self.B, self.n, self.w, self.h, self.dh,
                                                     L.stream()), 'local_attn_bwd')

@@ -1,0 +1,40 @@
+"""sample.py — drop-in for the reference CLI (lucidrains/progen sample.py:23-26: --seed, --checkpoint_path, --prime),
+plus --greedy (zero Gumbel noise: the deterministic mode the parity tests use).  Loads the newest checkpoint, rebuilds
+the model from its `model_config`, samples with top_k=25, add_bos=True (sample.py:70) and prints from prime_length on."""
+import click
+import numpy as np
+
+from progen_b200 import ProGen
+from progen_b200.checkpoint import get_checkpoint_fns
+from progen_b200.data import decode_tokens, encode_tokens
+from progen_b200.utils import sample
+
+
+@click.command()
+@click.option('--seed', default=42)
+@click.option('--checkpoint_path', default='./ckpts')
+@click.option('--prime', default='')
+@click.option('--greedy', default=False, is_flag=True)
+@click.option('--mixed_precision', default=False, is_flag=True)
+def main(seed, checkpoint_path, prime, greedy, mixed_precision):
+    _, get_last_checkpoint, _ = get_checkpoint_fns(checkpoint_path)
+    last_checkpoint = get_last_checkpoint()
+    if last_checkpoint is None:
+        exit(f'no checkpoints found at {checkpoint_path}')
+    params = last_checkpoint['params']
+    num_seqs = max(last_checkpoint['next_seq_index'], 0)
+    model_kwargs = last_checkpoint['model_config']
+    model = ProGen(**{**model_kwargs, 'mixed_precision': mixed_precision})
+    seq_len = model_kwargs['seq_len']
+    print(f'params: {sum(a.size for d in params.values() for a in d.values())}')
+    print(f'sequence length: {seq_len}')
+    print(f'trained for {num_seqs} sequences')
+    prime_tokens = encode_tokens(prime)
+    prime_length = len(prime_tokens) + 1
+    prime_tensor = np.array(prime_tokens, dtype=np.uint16)
+    sampled = sample(seed, model.apply, params, prime_tensor, seq_len, top_k=25, add_bos=True, greedy=greedy)
+    print('\n', prime, '\n', '*' * 40, '\n', decode_tokens(sampled[prime_length:]))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,48 @@
+"""Tensor-core local attention (attn_mma.cu) against a torch float64 reference of reference progen.py:88-102 computed
+from the same bf16 q|k|v, forward and backward, including window 0's zero look-back keys (quirk Q1)."""
+import pytest
+import torch
+
+from test_gpu_elementwise import attn_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('cfg', [(2, 256, 128, 2), (1, 512, 256, 3), (2, 192, 64, 2), (1, 1024, 256, 8), (3, 128, 128, 1)])
+def test_local_attn_mma_fwd_bwd(cfg):
+    from progen_b200 import lib as L
+    L.require_device()
+    B, n, w, h = cfg
+    dh = 64
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(n + w)
+    T, I = B * n, h * dh
+    qkv = (torch.randn(T, 3 * I, generator=g, device=dev) * 1.5).bfloat16()
+    out = torch.empty(T, I, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(T, h, device=dev)
+    L.check(L.load().progen_local_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, n, w, h, dh, L.stream()))
+    qd = qkv.double().requires_grad_(True)
+    ref = attn_ref(qd, B, n, w, h, dh)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-2, err
+    # lse against the fp32-exact CUDA-core kernel
+    out2 = torch.empty_like(out)
+    lse2 = torch.empty_like(lse)
+    L.check(L.load().progen_local_attn_fwd_simt(qkv.data_ptr(), out2.data_ptr(), lse2.data_ptr(), L.BF16, B, n, w, h, dh, L.stream()))
+    assert (lse - lse2).abs().max().item() < 2e-3
+    dout = torch.randn(T, I, generator=g, device=dev).bfloat16()
+    ref.backward(dout.double())
+    dqkv = torch.full_like(qkv, float('nan'))
+    delta = torch.empty(T, h, device=dev)
+    L.check(L.load().progen_local_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                           delta.data_ptr(), B, n, w, h, dh, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    gerr = (dqkv.double() - qd.grad).abs().max().item()
+    assert gerr < 4e-2 * max(1.0, qd.grad.abs().max().item()), (gerr, qd.grad.abs().max().item())
+    # per-part relative error (dq, dk, dv)
+    for part in range(3):
+        a = dqkv.double()[:, part * I:(part + 1) * I]
+        r = qd.grad[:, part * I:(part + 1) * I]
+        rel = (a - r).norm().item() / r.norm().item()
+        assert rel < 2e-2, (part, rel)
