@@ -110,7 +110,8 @@ int progen_local_attn_bwd_simt(const void* qkv, const void* out, const void* dou
 int progen_local_attn_fwd(const void* qkv, void* out, float* lse, int B, int seq_len, int window, int heads, int dim_head,
                           void* stream);
 int progen_local_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
-                          int B, int seq_len, int window, int heads, int dim_head, void* stream);
+                          const float* rot_sin, const float* rot_cos, int B, int seq_len, int window, int heads, int dim_head,
+                          void* stream);
 
 /* SGU gating — progen.py:182-184: out = xs * (Gp + spatial_biases[m]) and its backward (dxs, dGp, dbias) */
 int progen_sgu_gate_fwd(const void* xs, long long ldx, const void* gp, long long ldg, const float* bias, void* out,
@@ -130,6 +131,51 @@ int progen_grad_sqnorm(const float* g, long long n, float* workspace, float* out
 int progen_adamw_step(float* p, void* p_lp, const float* g, float* m, float* v, float* acc, long long n, long long n_decay,
                       const float* gnorm_sq, float lr, float b1, float b2, float eps, float wd, float max_norm,
                       long long step, int emit, void* stream);
+
+/* ---- KV-cached decode (BASELINE config 5; replaces the full re-forward per token of utils.py:115-117) ----
+ * Weights are TRANSPOSED copies ([out, in], fp32 or bf16 per `wdtype`); caches and scratch are fp32 device buffers owned
+ * by the caller.  `layers` is a HOST array of `depth` entries. */
+typedef struct progen_decode_layer_t {
+  int32_t kind;                /* 0 GLU, 1 GELU, 2 gMLP/SGU  (progen.py:210-212) */
+  int32_t _pad;
+  const float* ln1_scale;      /* [d] */
+  const void* wqkv_t;          /* [3*inner, d] */
+  const void* wo_t;            /* [d, inner] */
+  const float* bo;             /* [d] */
+  const float* ln2_scale;      /* [d] */
+  const void* win_t;           /* [2*hid | hid, d]; GLU: rows [0,hid) value, [hid,2hid) gate */
+  const float* bin;
+  const void* wout_t;          /* [d, hid | hid/2] */
+  const float* bout;           /* [d] */
+  const float* sgu_ln_scale;   /* [hid/2] */
+  const float* sgu_w;          /* [n, n] fp32 spatial_weights (row p is read up to column p) */
+  const float* sgu_b;          /* [n] */
+  const void* sgu_proj_t;      /* [hid/2, hid/2] */
+  const float* sgu_proj_b;
+  float* kcache;               /* [n, inner] rotated keys */
+  float* vcache;               /* [n, inner] rotated values */
+  float* shift1;               /* [d/2] previous position's LN half (attention block) */
+  float* shift2;               /* [d/2] previous position's LN half (feed-forward block) */
+  float* gn_hist;              /* [n, hid/2] normalised gate history (gMLP layers) */
+} progen_decode_layer_t;
+
+typedef struct progen_decode_t {
+  int32_t n, d, heads, dim_head, inner, window, hid, V, depth, wdtype, shift_tokens, top_k;
+  const float* embed;          /* [V, d] */
+  const float* lnf_scale;      /* [d] */
+  const void* whead_t;         /* [V, d] */
+  const float* bhead;          /* [V] */
+  const float* rot_sin;        /* [n, dim_head/2] */
+  const float* rot_cos;
+  const progen_decode_layer_t* layers;
+  int32_t* seq;                /* [n] device: token ids; sampled ids are ADDED in place (utils.py:129) */
+  int32_t* pos;                /* device scalar: position consumed by the next step */
+  const float* noise;          /* [n, V] gumbel noise, or NULL for the greedy limit */
+  float* logits_all;           /* [n, V] every step's logits (may be NULL) */
+  float *x, *y, *q, *att, *u, *gn, *sg, *pj, *logits;   /* scratch: d, d, inner, inner, 2*hid, hid/2, hid/2, hid/2, V */
+} progen_decode_t;
+
+int progen_decode_step(const progen_decode_t* model, int do_sample, void* stream);
 
 #ifdef __cplusplus
 }

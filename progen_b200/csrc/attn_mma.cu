@@ -11,6 +11,7 @@
 //
 // TODO(next round): move QK^T / PV to tcgen05 with S/P in TMEM (north_star); this mma.sync version is the correct,
 // fused, already-compute-bound stepping stone (attention is ~11% of the model FLOPs at d=512, w=256).
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/progen_b200.h"
 
@@ -110,11 +111,25 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-struct Dims { int n, w, h; };
+struct Dims {
+  int n, w, h;
+  const float* rot_sin;   // [n, 32]; when set, the backward kernels write gradients w.r.t. the UN-rotated q, k, v
+  const float* rot_cos;   //          (backward of apply_rotary_pos_emb, progen.py:36-41, fused into the epilogue)
+};
+
+// gradient of (x0 c - x1 s, x1 c + x0 s) w.r.t. (x0, x1): (d0 c + d1 s, d1 c - d0 s); pair index jj of position pos
+__device__ __forceinline__ uint32_t unrotate_pack(const Dims& dm, int pos, int jj, float d0, float d1) {
+  if (dm.rot_sin) {
+    const float s = __ldg(dm.rot_sin + pos * (DH / 2) + jj), c = __ldg(dm.rot_cos + pos * (DH / 2) + jj);
+    const float a = d0 * c + d1 * s, b = d1 * c - d0 * s;
+    d0 = a; d1 = b;
+  }
+  return pack_bf16x2(d0, d1);
+}
 
 // ================================================================================================ forward
 template <int BQ>
-__global__ void __launch_bounds__(BQ * 2) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+__global__ void __launch_bounds__(BQ * 2, 256 / BQ) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                               float* __restrict__ lse, const Dims dm) {
   constexpr int THREADS = BQ * 2;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -338,7 +353,8 @@ __global__ void __launch_bounds__(BQ * 2) attn_bwd_dq_mma_kernel(const bf16* __r
     const long long t = seq_row0 + q0 + warp * 16 + g + 8 * r;
     bf16* op = dqkv + t * ld + hh * DH + 2 * t4;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(op + 8 * j) = pack_bf16x2(dq[j][2 * r], dq[j][2 * r + 1]);
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint32_t*>(op + 8 * j) = unrotate_pack(dm, q0 + warp * 16 + g + 8 * r, 4 * j + t4, dq[j][2 * r], dq[j][2 * r + 1]);
   }
 }
 
@@ -451,14 +467,55 @@ __global__ void __launch_bounds__(BK * 2) attn_bwd_dkv_mma_kernel(const bf16* __
     bf16* pv = pk + I;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      *reinterpret_cast<uint32_t*>(pk + 8 * j) = pack_bf16x2(dk[j][2 * r], dk[j][2 * r + 1]);
-      *reinterpret_cast<uint32_t*>(pv + 8 * j) = pack_bf16x2(dv[j][2 * r], dv[j][2 * r + 1]);
+      const int pos = k0 + warp * 16 + g + 8 * r;
+      *reinterpret_cast<uint32_t*>(pk + 8 * j) = unrotate_pack(dm, pos, 4 * j + t4, dk[j][2 * r], dk[j][2 * r + 1]);
+      *reinterpret_cast<uint32_t*>(pv + 8 * j) = unrotate_pack(dm, pos, 4 * j + t4, dv[j][2 * r], dv[j][2 * r + 1]);
     }
   }
 }
 
 template <typename K> int set_smem(K kern, int bytes) {
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return PROGEN_OK;
+}
+
+// tile sizes: 128-row tiles need window % 128 == 0; PROGEN_ATTN_TILES="fwd,dq,dkv" (64|128 each) overrides for tuning
+struct TileChoice { int fwd, dq, dkv; };
+TileChoice tile_choice(int window) {
+  static TileChoice env = [] {
+    TileChoice t{64, 64, 64};      // measured on B200 at B=64, n=1024, w=256, h=8: 64-row tiles win (occupancy)
+    if (const char* e = getenv("PROGEN_ATTN_TILES")) sscanf(e, "%d,%d,%d", &t.fwd, &t.dq, &t.dkv);
+    return t;
+  }();
+  TileChoice t = env;
+  if (window % 128 != 0) t = TileChoice{64, 64, 64};
+  return t;
+}
+
+template <int BQ> int launch_fwd_t(const bf16* qkv, bf16* out, float* lse, const Dims& dm, int B, cudaStream_t s) {
+  const int smem = BQ * 128 + 4 * BKV * 128;
+  static bool once = false;
+  if (!once) { int rc = set_smem(attn_fwd_mma_kernel<BQ>, smem); if (rc) return rc; once = true; }
+  attn_fwd_mma_kernel<BQ><<<dim3(dm.n / BQ, dm.h, B), BQ * 2, smem, s>>>(qkv, out, lse, dm);
+  PG_LAUNCH_CHECK();
+  return PROGEN_OK;
+}
+template <int BQ> int launch_dq_t(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv,
+                                  const Dims& dm, int B, cudaStream_t s) {
+  const int smem = 2 * BQ * 128 + 4 * BKV * 128;
+  static bool once = false;
+  if (!once) { int rc = set_smem(attn_bwd_dq_mma_kernel<BQ>, smem); if (rc) return rc; once = true; }
+  attn_bwd_dq_mma_kernel<BQ><<<dim3(dm.n / BQ, dm.h, B), BQ * 2, smem, s>>>(qkv, dout, lse, delta, dqkv, dm);
+  PG_LAUNCH_CHECK();
+  return PROGEN_OK;
+}
+template <int BK> int launch_dkv_t(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv,
+                                   const Dims& dm, int B, cudaStream_t s) {
+  const int smem = 2 * BK * 128 + 4 * 64 * 128 + 4 * 64 * 4;
+  static bool once = false;
+  if (!once) { int rc = set_smem(attn_bwd_dkv_mma_kernel<BK>, smem); if (rc) return rc; once = true; }
+  attn_bwd_dkv_mma_kernel<BK><<<dim3(dm.n / BK, dm.h, B), BK * 2, smem, s>>>(qkv, dout, lse, delta, dqkv, dm);
+  PG_LAUNCH_CHECK();
   return PROGEN_OK;
 }
 
@@ -470,64 +527,30 @@ extern "C" {
 int progen_local_attn_fwd(const void* qkv, void* out, float* lse, int B, int seq_len, int window, int heads, int dim_head,
                           void* stream) {
   PG_CHECK_ARG(B > 0 && heads > 0 && dim_head == DH && window % 64 == 0 && seq_len % window == 0);
-  Dims dm{seq_len, window, heads};
+  Dims dm{seq_len, window, heads, nullptr, nullptr};
   cudaStream_t s = (cudaStream_t)stream;
-  if (window % 128 == 0) {
-    constexpr int BQ = 128;
-    const int smem = BQ * 128 + 4 * BKV * 128;
-    static bool once = false;
-    if (!once) { int rc = set_smem(attn_fwd_mma_kernel<BQ>, smem); if (rc) return rc; once = true; }
-    attn_fwd_mma_kernel<BQ><<<dim3(seq_len / BQ, heads, B), BQ * 2, smem, s>>>((const bf16*)qkv, (bf16*)out, lse, dm);
-  } else {
-    constexpr int BQ = 64;
-    const int smem = BQ * 128 + 4 * BKV * 128;
-    static bool once = false;
-    if (!once) { int rc = set_smem(attn_fwd_mma_kernel<BQ>, smem); if (rc) return rc; once = true; }
-    attn_fwd_mma_kernel<BQ><<<dim3(seq_len / BQ, heads, B), BQ * 2, smem, s>>>((const bf16*)qkv, (bf16*)out, lse, dm);
-  }
-  PG_LAUNCH_CHECK();
-  return PROGEN_OK;
+  if (tile_choice(window).fwd == 128) return launch_fwd_t<128>((const bf16*)qkv, (bf16*)out, lse, dm, B, s);
+  return launch_fwd_t<64>((const bf16*)qkv, (bf16*)out, lse, dm, B, s);
 }
 
-// dqkv [T, 3*heads*64] receives dq | dk | dv (gradients w.r.t. the ROTATED q, k, v); delta [T, heads] is workspace.
+// dqkv [T, 3*heads*64] receives dq | dk | dv; delta [T, heads] is workspace.  With rot_sin/rot_cos ([seq_len, 32] tables)
+// the rotary backward is fused and the gradients are w.r.t. the projections BEFORE rotary; with null tables they are
+// w.r.t. the rotated q, k, v.
 int progen_local_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
-                          int B, int seq_len, int window, int heads, int dim_head, void* stream) {
+                          const float* rot_sin, const float* rot_cos, int B, int seq_len, int window, int heads, int dim_head,
+                          void* stream) {
   PG_CHECK_ARG(B > 0 && heads > 0 && dim_head == DH && window % 64 == 0 && seq_len % window == 0);
-  Dims dm{seq_len, window, heads};
+  Dims dm{seq_len, window, heads, rot_sin, rot_cos};
   cudaStream_t s = (cudaStream_t)stream;
   const long long rows = (long long)B * seq_len * heads;
   attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, rows);
   PG_LAUNCH_CHECK();
-  if (window % 128 == 0) {
-    constexpr int BQ = 128;
-    const int smem_dq = 2 * BQ * 128 + 4 * BKV * 128;
-    const int smem_kv = 2 * BQ * 128 + 4 * 64 * 128 + 4 * 64 * 4;
-    static bool once = false;
-    if (!once) {
-      int rc = set_smem(attn_bwd_dq_mma_kernel<BQ>, smem_dq); if (rc) return rc;
-      rc = set_smem(attn_bwd_dkv_mma_kernel<BQ>, smem_kv); if (rc) return rc;
-      once = true;
-    }
-    attn_bwd_dq_mma_kernel<BQ><<<dim3(seq_len / BQ, heads, B), BQ * 2, smem_dq, s>>>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm);
-    PG_LAUNCH_CHECK();
-    attn_bwd_dkv_mma_kernel<BQ><<<dim3(seq_len / BQ, heads, B), BQ * 2, smem_kv, s>>>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm);
-    PG_LAUNCH_CHECK();
-  } else {
-    constexpr int BQ = 64;
-    const int smem_dq = 2 * BQ * 128 + 4 * BKV * 128;
-    const int smem_kv = 2 * BQ * 128 + 4 * 64 * 128 + 4 * 64 * 4;
-    static bool once = false;
-    if (!once) {
-      int rc = set_smem(attn_bwd_dq_mma_kernel<BQ>, smem_dq); if (rc) return rc;
-      rc = set_smem(attn_bwd_dkv_mma_kernel<BQ>, smem_kv); if (rc) return rc;
-      once = true;
-    }
-    attn_bwd_dq_mma_kernel<BQ><<<dim3(seq_len / BQ, heads, B), BQ * 2, smem_dq, s>>>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm);
-    PG_LAUNCH_CHECK();
-    attn_bwd_dkv_mma_kernel<BQ><<<dim3(seq_len / BQ, heads, B), BQ * 2, smem_kv, s>>>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm);
-    PG_LAUNCH_CHECK();
-  }
-  return PROGEN_OK;
+  const TileChoice tc = tile_choice(window);
+  int rc = tc.dq == 128 ? launch_dq_t<128>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s)
+                        : launch_dq_t<64>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s);
+  if (rc) return rc;
+  return tc.dkv == 128 ? launch_dkv_t<128>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s)
+                       : launch_dkv_t<64>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s);
 }
 
 }  // extern "C"

@@ -84,6 +84,27 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 
+// Same functions with the hardware tanh (MUFU.TANH, rel. error ~2^-11): used where the result is rounded to bf16 anyway
+// (tensor-core path); the fp32 parity path keeps tanhf.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool FAST> __device__ __forceinline__ float gelu_fwd(float x) {
+  if constexpr (!FAST) return gelu_tanh(x);
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanh_fast(u));
+}
+template <bool FAST> __device__ __forceinline__ float gelu_bwd(float x) {
+  if constexpr (!FAST) return gelu_tanh_grad(x);
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_fast(k0 * (x + k1 * x * x2));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
+}
+
 // vector load/store of NV consecutive elements (NV * sizeof(T) must be a multiple of 16 bytes, pointer aligned)
 template <int NV> __device__ __forceinline__ void load_vec(const float* p, float (&v)[NV]) {
 #pragma unroll

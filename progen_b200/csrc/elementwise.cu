@@ -183,13 +183,22 @@ __global__ void ln_shift_bwd_kernel(const TO* __restrict__ dy, long long lddy, c
       }
     }
   }
+  // dscale: reduce the 8 warps of the block through shared memory (128 columns at a time), one atomic per column per block
+  __shared__ float red[ROWS_PER_BLOCK][128];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
-    const int c = ch * 128 + lane * 4;
-    if (c < d) {
+    if (ch * 128 >= d) break;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(dscale + c + i, ds_acc[ch][i]);
+    for (int i = 0; i < 4; ++i) red[warp][lane * 4 + i] = ds_acc[ch][i];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROWS_PER_BLOCK; ++w) s += red[w][threadIdx.x];
+      const int c = ch * 128 + threadIdx.x;
+      if (c < d) atomicAdd(dscale + c, s);
     }
+    __syncthreads();
   }
 }
 
@@ -463,7 +472,9 @@ int progen_ln_shift_bwd(const void* dy, long long lddy, int act_dtype, const voi
   PG_CHECK_ARG(residual ? (dres != nullptr && x_dtype == PG_F32) : (dout != nullptr));
   cudaStream_t s = (cudaStream_t)stream;
   long long b = (T + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
-  const int grid = (int)(b > pg_num_sms() * 2 ? pg_num_sms() * 2 : b);
+  // row-per-warp with two dependent passes is latency-bound: keep several CTAs resident per SM (grid = k * #SMs)
+  const int per_sm = d <= 1024 ? 6 : 3;
+  const int grid = (int)(b > pg_num_sms() * per_sm ? pg_num_sms() * per_sm : b);
   const int nch = (d + 127) / 128;
 #define LN_BWD_N(TI, TO, NCH, RES) ln_shift_bwd_kernel<TI, TO, NCH, RES><<<grid, 256, 0, s>>>((const TO*)dy, lddy, (const TI*)x, ldx, scale, mean, rstd, dres, (TO*)dout, ldo, dscale, T, d, seq_len, shift)
 #define LN_BWD(TI, TO, RES) do { if (nch <= 4) LN_BWD_N(TI, TO, 4, RES); else if (nch <= 8) LN_BWD_N(TI, TO, 8, RES); \

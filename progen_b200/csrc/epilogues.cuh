@@ -29,59 +29,173 @@ struct EpiArgs {
   int tril_rows;
 };
 
-template <int KIND, typename TO, int NV>
-__device__ __forceinline__ void epi_apply(const EpiArgs& e, long long row, int col, float (&v)[NV]) {
+// ---------------------------------------------------------------------------------------------------------
+// How an epilogue thread moves its row slice to / from global memory.
+//   DirectIO      : per-thread vector accesses (CUDA-core GEMM: 8 consecutive columns per thread)
+//   WarpStagedIO  : the tcgen05 epilogue owns one ROW per lane (TMEM lane == row), so direct stores would touch 32
+//                   different 128-byte lines per instruction (LSU wavefront bound).  Instead the warp transposes 64-byte
+//                   row slices through a private shared-memory buffer so each instruction moves 8 rows x 64 contiguous
+//                   bytes; same for the loads of residual / saved pre-activations.
+struct DirectIO {
+  template <int N, typename T> __device__ __forceinline__ void store(T* p, long long, const float (&v)[N], bool valid) const {
+    if (valid) store_vec<N>(p, v);
+  }
+  template <int N, typename T> __device__ __forceinline__ void load(const T* p, long long, float (&v)[N], bool valid) const {
+    if (valid) load_vec<N>(p, v);
+    else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = 0.f;
+    }
+  }
+};
+
+constexpr int STAGE_ROW_BYTES = 80;                      // 64 B payload + 16 B pad (bank spread)
+constexpr int STAGE_WARP_BYTES = 32 * STAGE_ROW_BYTES;   // 2560 B per epilogue warp
+
+struct WarpStagedIO {
+  uint8_t* buf;          // this warp's staging buffer (generic pointer into shared memory)
+  int lane;
+  unsigned valid_mask;   // bit r: row r of this warp's 32-row block is inside the matrix
+
+  template <typename T> static __device__ __forceinline__ uint4 pack16(const float* v) {
+    uint4 t;
+    if constexpr (sizeof(T) == 2) {
+      t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+    } else {
+      t.x = __float_as_uint(v[0]); t.y = __float_as_uint(v[1]); t.z = __float_as_uint(v[2]); t.w = __float_as_uint(v[3]);
+    }
+    return t;
+  }
+  template <typename T> static __device__ __forceinline__ void unpack16(const uint4& t, float* v) {
+    if constexpr (sizeof(T) == 2) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    } else {
+      v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+    }
+  }
+
+  // p: this lane's (row, col) element; rows of the warp are consecutive, `ld` elements apart
+  template <int N, typename T> __device__ __forceinline__ void store(T* p, long long ld, const float (&v)[N], bool) const {
+    constexpr int BYTES = N * (int)sizeof(T);
+    constexpr int SW = BYTES < 64 ? BYTES : 64;          // slice width in bytes per pass
+    constexpr int PPR = SW / 16;                         // 16-byte pieces per row slice
+    constexpr int EPP = 16 / (int)sizeof(T);             // elements per piece
+    uint8_t* base = reinterpret_cast<uint8_t*>(p - (long long)lane * ld);
+#pragma unroll
+    for (int s = 0; s < BYTES / SW; ++s) {
+#pragma unroll
+      for (int q = 0; q < PPR; ++q)
+        *reinterpret_cast<uint4*>(buf + lane * STAGE_ROW_BYTES + q * 16) = pack16<T>(&v[s * (SW / (int)sizeof(T)) + q * EPP]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < PPR; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = idx / PPR, q = idx % PPR;
+        if ((valid_mask >> r) & 1u) {
+          const uint4 t = *reinterpret_cast<const uint4*>(buf + r * STAGE_ROW_BYTES + q * 16);
+          *reinterpret_cast<uint4*>(base + (long long)r * ld * (int)sizeof(T) + s * SW + q * 16) = t;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  template <int N, typename T> __device__ __forceinline__ void load(const T* p, long long ld, float (&v)[N], bool) const {
+    constexpr int BYTES = N * (int)sizeof(T);
+    constexpr int SW = BYTES < 64 ? BYTES : 64;
+    constexpr int PPR = SW / 16;
+    constexpr int EPP = 16 / (int)sizeof(T);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(p - (long long)lane * ld);
+#pragma unroll
+    for (int s = 0; s < BYTES / SW; ++s) {
+#pragma unroll
+      for (int it = 0; it < PPR; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = idx / PPR, q = idx % PPR;
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if ((valid_mask >> r) & 1u) t = *reinterpret_cast<const uint4*>(base + (long long)r * ld * (int)sizeof(T) + s * SW + q * 16);
+        *reinterpret_cast<uint4*>(buf + r * STAGE_ROW_BYTES + q * 16) = t;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < PPR; ++q)
+        unpack16<T>(*reinterpret_cast<const uint4*>(buf + lane * STAGE_ROW_BYTES + q * 16), &v[s * (SW / (int)sizeof(T)) + q * EPP]);
+      __syncwarp();
+    }
+  }
+};
+
+// Every lane of the calling warp must enter (staged IO is warp-cooperative); `valid` says whether this lane's row exists.
+template <int KIND, typename TO, int NV, typename IO>
+__device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long long row, int col, float (&v)[NV], bool valid) {
+  constexpr bool FAST = sizeof(TO) == 2;      // bf16 outputs: hardware tanh is below the output rounding
   if constexpr (KIND == EPI_STORE) {
     if (e.bias) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + col + i);
     }
-    store_vec<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, v);
+    io.template store<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, e.ldo, v, valid);
   } else if constexpr (KIND == EPI_ROTARY) {
     const int pos = (int)(row % e.seq_len);
     const int half = e.dim_head >> 1;
     const float* sp = e.rot_sin + (long long)pos * half;
     const float* cp = e.rot_cos + (long long)pos * half;
     float o[NV];
+    if (e.dim_head % NV == 0) {
+      // the NV columns sit inside one head: NV/2 consecutive (sin, cos) entries, 16-byte vector loads
+      const int j0 = (col % e.dim_head) >> 1;
+      float s[NV / 2], c[NV / 2];
+      load_vec<NV / 2>(sp + j0, s);
+      load_vec<NV / 2>(cp + j0, c);
 #pragma unroll
-    for (int i = 0; i < NV; i += 2) {
-      const int j = ((col + i) % e.dim_head) >> 1;
-      const float s = __ldg(sp + j), c = __ldg(cp + j);
-      o[i] = v[i] * c - v[i + 1] * s;
-      o[i + 1] = v[i + 1] * c + v[i] * s;
+      for (int i = 0; i < NV; i += 2) {
+        o[i] = v[i] * c[i >> 1] - v[i + 1] * s[i >> 1];
+        o[i + 1] = v[i + 1] * c[i >> 1] + v[i] * s[i >> 1];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; i += 2) {
+        const int j = ((col + i) % e.dim_head) >> 1;
+        const float s = __ldg(sp + j), c = __ldg(cp + j);
+        o[i] = v[i] * c - v[i + 1] * s;
+        o[i + 1] = v[i + 1] * c + v[i] * s;
+      }
     }
-    store_vec<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, o);
+    io.template store<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, e.ldo, o, valid);
   } else if constexpr (KIND == EPI_RESIDUAL) {
     // out = residual_in + acc + bias; residual_in = aux (fp32, ldaux) when given, else out itself (in place)
     float* p = reinterpret_cast<float*>(e.out) + row * e.ldo + col;
-    const float* pin = e.aux ? reinterpret_cast<const float*>(e.aux) + row * e.ldaux + col : p;
     float r[NV];
-    load_vec<NV>(pin, r);
+    if (e.aux) io.template load<NV>(reinterpret_cast<const float*>(e.aux) + row * e.ldaux + col, e.ldaux, r, valid);
+    else io.template load<NV>(const_cast<const float*>(p), e.ldo, r, valid);
 #pragma unroll
     for (int i = 0; i < NV; ++i) r[i] += v[i] + (e.bias ? __ldg(e.bias + col + i) : 0.f);
-    store_vec<NV>(p, r);
+    io.template store<NV>(p, e.ldo, r, valid);
   } else if constexpr (KIND == EPI_GLU) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + col + i);
-    store_vec<NV>(reinterpret_cast<TO*>(e.out2) + row * e.ldo2 + col, v);
+    io.template store<NV>(reinterpret_cast<TO*>(e.out2) + row * e.ldo2 + col, e.ldo2, v, valid);
     TO* po = reinterpret_cast<TO*>(e.out) + row * e.ldo + (col >> 1);
     if constexpr (NV >= 16) {
       float o[NV / 2];
 #pragma unroll
-      for (int i = 0; i < NV / 2; ++i) o[i] = v[2 * i] * gelu_tanh(v[2 * i + 1]);
-      store_vec<NV / 2>(po, o);
+      for (int i = 0; i < NV / 2; ++i) o[i] = v[2 * i] * gelu_fwd<FAST>(v[2 * i + 1]);
+      io.template store<NV / 2>(po, e.ldo, o, valid);
     } else {
+      if (valid) {
 #pragma unroll
-      for (int i = 0; i < NV / 2; ++i) po[i] = from_f32<TO>(v[2 * i] * gelu_tanh(v[2 * i + 1]));
+        for (int i = 0; i < NV / 2; ++i) po[i] = from_f32<TO>(v[2 * i] * gelu_fwd<FAST>(v[2 * i + 1]));
+      }
     }
   } else if constexpr (KIND == EPI_GELU) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + col + i);
-    store_vec<NV>(reinterpret_cast<TO*>(e.out2) + row * e.ldo2 + col, v);
+    io.template store<NV>(reinterpret_cast<TO*>(e.out2) + row * e.ldo2 + col, e.ldo2, v, valid);
     float o[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) o[i] = gelu_tanh(v[i]);
-    store_vec<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, o);
+    for (int i = 0; i < NV; ++i) o[i] = gelu_fwd<FAST>(v[i]);
+    io.template store<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, e.ldo, o, valid);
   } else if constexpr (KIND == EPI_GLU_BWD) {
     // acc column c is d(h[c]); pre-activations of (value, gate) sit at aux[2c], aux[2c+1]
     const TO* pa = reinterpret_cast<const TO*>(e.aux) + row * e.ldaux + 2 * col;
@@ -89,22 +203,23 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, long long row, int c
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float u[NV], o[NV];
-      load_vec<NV>(pa + h * NV, u);
+      io.template load<NV>(pa + h * NV, e.ldaux, u, valid);
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
         const float dh = v[h * (NV / 2) + (i >> 1)];
-        o[i] = dh * gelu_tanh(u[i + 1]);
-        o[i + 1] = dh * u[i] * gelu_tanh_grad(u[i + 1]);
+        o[i] = dh * gelu_fwd<FAST>(u[i + 1]);
+        o[i + 1] = dh * u[i] * gelu_bwd<FAST>(u[i + 1]);
       }
-      store_vec<NV>(po + h * NV, o);
+      io.template store<NV>(po + h * NV, e.ldo, o, valid);
     }
   } else if constexpr (KIND == EPI_GELU_BWD) {
     float u[NV];
-    load_vec<NV>(reinterpret_cast<const TO*>(e.aux) + row * e.ldaux + col, u);
+    io.template load<NV>(reinterpret_cast<const TO*>(e.aux) + row * e.ldaux + col, e.ldaux, u, valid);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] *= gelu_tanh_grad(u[i]);
-    store_vec<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, v);
+    for (int i = 0; i < NV; ++i) v[i] *= gelu_bwd<FAST>(u[i]);
+    io.template store<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, e.ldo, v, valid);
   } else if constexpr (KIND == EPI_ACCUM) {
+    if (!valid) return;
     float* p = reinterpret_cast<float*>(e.out) + row * e.ldo + col;
     const int lim = e.tril ? (int)(row % e.tril_rows) : 0x7fffffff;
     if (e.atomic) {

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
     const int m = m0 + ty * 8 + i;
     if (m >= g.M) break;
     const long long row = (g.batch_reduce ? 0 : (long long)z * g.d_batch_rows) + m;
-    epi_apply<KIND, TO, 8>(g.epi, row, col, acc[i]);
+    epi_apply<KIND, TO, 8>(g.epi, DirectIO{}, row, col, acc[i], true);
   }
 }
 

@@ -19,7 +19,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;           // 4 control warps + 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 template <int BN> struct TileCfg {
@@ -28,7 +29,8 @@ template <int BN> struct TileCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;   // 6 (BN=128) / 4 (BN=256)
   static constexpr int TMEM_COLS = 2 * BN;              // 256 / 512
-  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + NUM_EPI_WARPS * STAGE_WARP_BYTES;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -190,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);            // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), NUM_EPI_WARPS);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -270,8 +272,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue (warps 4..7 <-> TMEM lanes 0..127)
-    const int q = warp & 3;
+    const int q = warp & 3;                    // TMEM lane quarter this warp may touch
+    const int chalf = (warp - 4) >> 2;         // which half of the tile columns this warp drains
     const int r_in_tile = q * 32 + lane;
+    WarpStagedIO io;
+    io.buf = smem_raw + (bar_base - smem_u32(smem_raw)) + Cfg::BAR_BYTES + (warp - 4) * STAGE_WARP_BYTES;
+    io.lane = lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     TileInfo ti;
@@ -282,8 +288,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const long long row = (g.batch_reduce ? 0 : (long long)ti.z * g.d_batch_rows) + m;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       const bool has_k = ti.kb_end > ti.kb_begin;
+      const bool valid = m < g.M;
+      io.valid_mask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int col = ti.n0 + c * 32;
         if (col >= g.N) break;                          // warp-uniform
         float v[32];
@@ -292,7 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (m < g.M) epi_apply<KIND, TO, 32>(g.epi, row, col, v);
+        epi_apply<KIND, TO, 32>(g.epi, io, row, col, v, valid);
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -334,9 +334,9 @@ class Engine:
     def attn_bwd(self, qkv, out, dout, lse, dqkv):
         if self.attn_tc:
             L.check(self.lib.progen_local_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                                   self.delta.data_ptr(), self.B, self.n, self.w, self.h, self.dh, L.stream()),
-                    'local_attn_bwd')
-            return
+                                                   self.delta.data_ptr(), self.rot_sin.data_ptr(), self.rot_cos.data_ptr(), self.B,
+                                                   self.n, self.w, self.h, self.dh, L.stream()), 'local_attn_bwd')
+            return     # rotary backward is fused into the kernel's epilogue
         L.check(self.lib.progen_local_attn_bwd_simt(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                                     self.delta.data_ptr(), self.act_dt, self.B, self.n, self.w, self.h, self.dh,
                                                     L.stream()), 'local_attn_bwd')
@@ -436,8 +436,9 @@ class Engine:
             self.wgrad_gemm(s['att'], I, dres_lp, d, self.G(a + 'linear_1', 'w'))
             self.dgrad_gemm(dres_lp, d, self.W(a + 'linear_1', 'w'), I, self.datt)
             self.attn_bwd(s['qkv'], s['att'], self.datt, s['lse'], self.dqkv)
-            L.check(lib.progen_rotary_bwd(self.dqkv.data_ptr(), 3 * I, self.act_dt, self.rot_sin.data_ptr(), self.rot_cos.data_ptr(),
-                                          T, 3 * I, n, self.dh, st), 'rotary_bwd')
+            if not self.attn_tc:
+                L.check(lib.progen_rotary_bwd(self.dqkv.data_ptr(), 3 * I, self.act_dt, self.rot_sin.data_ptr(),
+                                              self.rot_cos.data_ptr(), T, 3 * I, n, self.dh, st), 'rotary_bwd')
             self.wgrad_gemm(s['y1'], d, self.dqkv, 3 * I, self.G(a + 'linear', 'w'))
             self.dgrad_gemm(self.dqkv, 3 * I, self.W(a + 'linear', 'w'), d, self.dy)
             self.ln_bwd_res(self.dy, x0, self.Pf(a + 'layer_norm', 'scale'), s['mean1'], s['rstd1'], self.G(a + 'layer_norm', 'scale'), shift)

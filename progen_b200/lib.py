@@ -56,12 +56,13 @@ PROTOTYPES = {
     'progen_local_attn_fwd_simt': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'progen_local_attn_bwd_simt': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'progen_local_attn_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    'progen_local_attn_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'progen_local_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'progen_sgu_gate_fwd': [_P, _LL, _P, _LL, _P, _P, _LL, _I, _LL, _I, _I, _P],
     'progen_sgu_gate_bwd': [_P, _LL, _P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _I, _LL, _I, _I, _P],
     'progen_gelu_bwd': [_P, _P, _I, _LL, _P],
     'progen_cast_f32': [_P, _P, _I, _LL, _P],
     'progen_tril_cast': [_P, _P, _I, _I, _P],
+    'progen_decode_step': [_P, _I, _P],
     'progen_optim_workspace_floats': [],
     'progen_grad_sqnorm': [_P, _LL, _P, _P, _P],
     'progen_adamw_step': [_P, _P, _P, _P, _P, _P, _LL, _LL, _P, _F, _F, _F, _F, _F, _F, _LL, _I, _P],

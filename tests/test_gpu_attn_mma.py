@@ -35,7 +35,7 @@ def test_local_attn_mma_fwd_bwd(cfg):
     dqkv = torch.full_like(qkv, float('nan'))
     delta = torch.empty(T, h, device=dev)
     L.check(L.load().progen_local_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                           delta.data_ptr(), B, n, w, h, dh, L.stream()))
+                                           delta.data_ptr(), 0, 0, B, n, w, h, dh, L.stream()))
     torch.cuda.synchronize()
     assert torch.isfinite(dqkv.float()).all()
     gerr = (dqkv.double() - qd.grad).abs().max().item()
@@ -46,3 +46,17 @@ def test_local_attn_mma_fwd_bwd(cfg):
         r = qd.grad[:, part * I:(part + 1) * I]
         rel = (a - r).norm().item() / r.norm().item()
         assert rel < 2e-2, (part, rel)
+    # fused rotary backward == separate rotary_bwd kernel applied to the un-fused result
+    from gemm_cases import rotary_tables
+    sin, cos = rotary_tables(n, dh, dev)
+    fused = torch.empty_like(qkv)
+    L.check(L.load().progen_local_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), fused.data_ptr(),
+                                           delta.data_ptr(), sin.data_ptr(), cos.data_ptr(), B, n, w, h, dh, L.stream()))
+    ref2 = torch.stack((dqkv.double()[:, 0::2], dqkv.double()[:, 1::2]), dim=-1)
+    pos = torch.arange(T, device=dev) % n
+    s_ = sin.double()[pos].repeat(1, 3 * h)
+    c_ = cos.double()[pos].repeat(1, 3 * h)
+    exp0 = ref2[..., 0] * c_ + ref2[..., 1] * s_
+    exp1 = ref2[..., 1] * c_ - ref2[..., 0] * s_
+    expect = torch.stack((exp0, exp1), dim=-1).flatten(-2)
+    assert (fused.double() - expect).abs().max().item() < 3e-2 * max(1.0, expect.abs().max().item())
