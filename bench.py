@@ -106,17 +106,26 @@ def synthetic_batches(count, B, n, seed):
     return out
 
 
-def cpu_port_tokens_per_sec(kw, steps, warmup, rows=2, seed=123):
+CPU_THREAD_CAP = 32      # the box reports 128 logical CPUs shared with other tenants; 128 torch threads thrash (6-52 tok/s)
+
+
+def cpu_threads():
+    return max(1, min(len(os.sched_getaffinity(0)), CPU_THREAD_CAP))
+
+
+def cpu_port_tokens_per_sec(kw, steps, warmup, rows=1, seed=123, budget_s=60.0):
     """The reference's Jax path is not installable (no jax wheels, no network), so the timed CPU implementation is the
-    oracle's torch port of the same algorithm: fp32, all host cores through torch intra-op threads, fwd + bwd."""
+    oracle's torch port of the same algorithm: fp32, host cores through torch intra-op threads, fwd + bwd.
+    Bounded: stops as soon as `budget_s` of timed work has accumulated (a slow warm-up step counts as the sample)."""
     from oracle import progen_ref as O
     from oracle import progen_torch as T
+    torch.set_num_threads(cpu_threads())
     cfg = O.make_config(**kw)
     params = O.init_params(cfg, 0)
     prm = T.to_torch(params, torch.float32, requires_grad=True)
     rng = np.random.default_rng(seed)
     n = cfg['seq_len']
-    times = []
+    times, first = [], None
     for i in range(warmup + steps):
         data = torch.as_tensor(rng.integers(0, 256, (rows, n + 1)).astype(np.int64))
         t0 = time.perf_counter()
@@ -126,8 +135,13 @@ def cpu_port_tokens_per_sec(kw, steps, warmup, rows=2, seed=123):
             for v in d.values():
                 v.grad = None
         dt = time.perf_counter() - t0
+        first = dt if first is None else first
         if i >= warmup:
             times.append(dt)
+        if sum(times) + (first if not times else 0.0) > budget_s:
+            break
+    if not times:
+        times = [first]
     sec = sum(times) / len(times)
     return rows * n / sec, sec, rows
 
@@ -137,13 +151,12 @@ def run_reference_arm(args, cfgd):
     if rank != 0:
         return
     kw = cfgd['kwargs']
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
+    cores = cpu_threads()
     # bounded sample: one sequence per step, at most 3 timed steps + 1 warm-up (~40 s each on the box host cores)
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     tps, sec, rows = cpu_port_tokens_per_sec(kw, steps, warmup, rows=1)
     sample = f"{rows} sequence x {kw['seq_len']} tokens per step (fwd+bwd, fp32), {steps} timed steps (of --steps {args.steps})"
-    line = dict(impl='reference', metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=0, steps=args.steps,
+    line = dict(impl='reference', metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', config=dict(workload=cfgd['name']),
                 cpu_baseline=dict(value=tps, unit='tokens/s', cores=cores, kind='port', sample=sample),
@@ -287,8 +300,7 @@ def main():
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline, final_loss=final_loss)
         if not args.no_cpu_baseline and world == 1:
-            cores = len(os.sched_getaffinity(0))
-            torch.set_num_threads(cores)
+            cores = cpu_threads()
             v, sec, rows = cpu_port_tokens_per_sec(kw, steps=1, warmup=1, rows=1)
             line['cpu_baseline'] = dict(value=v, unit='tokens/s', cores=cores, kind='port',
                                         sample=f'{rows} sequences x {n} tokens, fwd+bwd fp32, 1 timed step ({sec:.1f} s)')

@@ -81,10 +81,13 @@ int progen_embed_bwd(const int* tokens, const float* dx, float* dtable, long lon
  * Saves mean / rstd per row for the backward pass. */
 int progen_ln_shift_fwd(const void* x, long long ldx, int x_dtype, const float* scale, void* y, long long ldy, int y_dtype,
                         float* mean, float* rstd, long long T, int d, int seq_len, int shift, void* stream);
-/* backward of the above; residual=1 accumulates into the fp32 residual gradient `dres` [T,d] and mirrors it to `dout`. */
+/* backward of the above; residual=1 accumulates into the fp32 residual gradient `dres` [T,d] and mirrors it to `dout`;
+ * `dres_colsum` (nullable, residual only) += column sums of the updated dres = the bias gradient of the Linear that
+ * produced this residual branch's input (saves a separate pass over dres). */
 int progen_ln_shift_bwd(const void* dy, long long lddy, int act_dtype, const void* x, long long ldx, int x_dtype,
                         const float* scale, const float* mean, const float* rstd, float* dres, void* dout, long long ldo,
-                        float* dscale, long long T, int d, int seq_len, int shift, int residual, void* stream);
+                        float* dscale, float* dres_colsum, long long T, int d, int seq_len, int shift, int residual,
+                        void* stream);
 
 /* out[c] += sum_t in[t,c] — bias gradients of every hk.Linear */
 int progen_colsum(const void* in, long long ld, int dtype, float* out, long long T, int N, void* stream);

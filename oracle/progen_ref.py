@@ -220,7 +220,8 @@ def feed_forward(x, prm, i, cfg, kind):
 def forward(params, seq, cfg, dtype=np.float64):
     """`model.apply(params, rng, seq)` for ONE sequence — progen.py:224-233.  seq: (n,) ints -> (n, num_tokens)."""
     prm = {m: {k: v.astype(dtype) for k, v in d.items()} for m, d in params.items()}
-    seq = np.asarray(seq).astype(np.int64)
+    # jax clamps out-of-range gather indices (hk.Embed -> embeddings[ids]); reachable through the add_bos quirk (Q5)
+    seq = np.clip(np.asarray(seq).astype(np.int64), 0, cfg['num_tokens'] - 1)
     n = seq.shape[0]
     x = prm[P + 'embed']['embeddings'][seq]
     sin, cos = fixed_pos_embedding(n, cfg['dim_head'], dtype)

@@ -60,7 +60,7 @@ def forward(prm, ids, cfg, operand_round=None):
     B, n = ids.shape
     h, dh, w = cfg['heads'], cfg['dim_head'], cfg['window_size']
     W = n // w
-    x = prm[P + 'embed']['embeddings'][ids]
+    x = prm[P + 'embed']['embeddings'][ids.clamp(0, cfg['num_tokens'] - 1)]     # jax gather clamps
     dtype = x.dtype
     sin, cos = _rotary_tables(n, dh, dtype)
     mask = torch.tril(torch.ones(w, 2 * w, dtype=torch.bool), w)

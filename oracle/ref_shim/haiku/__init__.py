@@ -122,7 +122,7 @@ class Embed(Module):
     def __call__(self, ids):
         emb = get_parameter('embeddings', (self.vocab_size, self.embed_dim),
                             init=self.w_init or initializers.TruncatedNormal(stddev=1.0))
-        return emb[np.asarray(ids).astype(np.int64)]
+        return emb[np.clip(np.asarray(ids).astype(np.int64), 0, self.vocab_size - 1)]     # jax gather clamps
 
 
 class LayerNorm(Module):

@@ -121,14 +121,19 @@ template <typename TI, typename TO, int NCH, bool RESIDUAL>
 __global__ void ln_shift_bwd_kernel(const TO* __restrict__ dy, long long lddy, const TI* __restrict__ x, long long ldx,
                                     const float* __restrict__ scale, const float* __restrict__ mean_in,
                                     const float* __restrict__ rstd_in, float* __restrict__ dres, TO* __restrict__ dout,
-                                    long long ldo, float* __restrict__ dscale, long long T, int d, int seq_len, int shift) {
+                                    long long ldo, float* __restrict__ dscale, float* __restrict__ dres_colsum,
+                                    long long T, int d, int seq_len, int shift) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = d >> 1;
   float ds_acc[NCH][4];
+  float cs_acc[RESIDUAL ? NCH : 1][4];       // column sums of the UPDATED residual gradient (= the next bias gradient)
 #pragma unroll
   for (int i = 0; i < NCH; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ds_acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      ds_acc[i][j] = 0.f;
+      if (RESIDUAL) cs_acc[RESIDUAL ? i : 0][j] = 0.f;
+    }
 
   for (long long t = blockIdx.x * (long long)ROWS_PER_BLOCK + warp; t < T; t += (long long)gridDim.x * ROWS_PER_BLOCK) {
     const TI* xr = x + t * ldx;
@@ -174,7 +179,7 @@ __global__ void ln_shift_bwd_kernel(const TO* __restrict__ dy, long long lddy, c
           float r[4];
           load4<float>(dres + t * (long long)d + c, r);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) r[i] += o[i];
+          for (int i = 0; i < 4; ++i) { r[i] += o[i]; cs_acc[ch][i] += r[i]; }
           store4(dres + t * (long long)d + c, r);
           if (dout) store4(dout + t * ldo + c, r);
         } else {
@@ -199,6 +204,21 @@ __global__ void ln_shift_bwd_kernel(const TO* __restrict__ dy, long long lddy, c
       if (c < d) atomicAdd(dscale + c, s);
     }
     __syncthreads();
+    if constexpr (RESIDUAL) {
+      if (dres_colsum) {                       // block-uniform
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[warp][lane * 4 + i] = cs_acc[ch][i];
+        __syncthreads();
+        if (threadIdx.x < 128) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < ROWS_PER_BLOCK; ++w) s += red[w][threadIdx.x];
+          const int c = ch * 128 + threadIdx.x;
+          if (c < d) atomicAdd(dres_colsum + c, s);
+        }
+        __syncthreads();
+      }
+    }
   }
 }
 
@@ -467,7 +487,8 @@ int progen_ln_shift_fwd(const void* x, long long ldx, int x_dtype, const float* 
 // residual == 0: dout[t*ldo + c] = dx.
 int progen_ln_shift_bwd(const void* dy, long long lddy, int act_dtype, const void* x, long long ldx, int x_dtype,
                         const float* scale, const float* mean, const float* rstd, float* dres, void* dout, long long ldo,
-                        float* dscale, long long T, int d, int seq_len, int shift, int residual, void* stream) {
+                        float* dscale, float* dres_colsum, long long T, int d, int seq_len, int shift, int residual,
+                        void* stream) {
   PG_CHECK_ARG(T > 0 && d % 8 == 0 && d <= 4096 && seq_len > 0 && T % seq_len == 0);
   PG_CHECK_ARG(residual ? (dres != nullptr && x_dtype == PG_F32) : (dout != nullptr));
   cudaStream_t s = (cudaStream_t)stream;
@@ -476,7 +497,7 @@ int progen_ln_shift_bwd(const void* dy, long long lddy, int act_dtype, const voi
   const int per_sm = d <= 1024 ? 6 : 3;
   const int grid = (int)(b > pg_num_sms() * per_sm ? pg_num_sms() * per_sm : b);
   const int nch = (d + 127) / 128;
-#define LN_BWD_N(TI, TO, NCH, RES) ln_shift_bwd_kernel<TI, TO, NCH, RES><<<grid, 256, 0, s>>>((const TO*)dy, lddy, (const TI*)x, ldx, scale, mean, rstd, dres, (TO*)dout, ldo, dscale, T, d, seq_len, shift)
+#define LN_BWD_N(TI, TO, NCH, RES) ln_shift_bwd_kernel<TI, TO, NCH, RES><<<grid, 256, 0, s>>>((const TO*)dy, lddy, (const TI*)x, ldx, scale, mean, rstd, dres, (TO*)dout, ldo, dscale, dres_colsum, T, d, seq_len, shift)
 #define LN_BWD(TI, TO, RES) do { if (nch <= 4) LN_BWD_N(TI, TO, 4, RES); else if (nch <= 8) LN_BWD_N(TI, TO, 8, RES); \
     else if (nch <= 16) LN_BWD_N(TI, TO, 16, RES); else LN_BWD_N(TI, TO, 32, RES); } while (0)
   if (residual) {

@@ -106,16 +106,28 @@ struct WarpStagedIO {
     constexpr int SW = BYTES < 64 ? BYTES : 64;
     constexpr int PPR = SW / 16;
     constexpr int EPP = 16 / (int)sizeof(T);
+    constexpr int PASSES = BYTES / SW;
     const uint8_t* base = reinterpret_cast<const uint8_t*>(p - (long long)lane * ld);
+    // issue every global load of every pass first (memory-level parallelism), then transpose pass by pass
+    uint4 t[PASSES][PPR];
 #pragma unroll
-    for (int s = 0; s < BYTES / SW; ++s) {
+    for (int s = 0; s < PASSES; ++s) {
 #pragma unroll
       for (int it = 0; it < PPR; ++it) {
         const int idx = it * 32 + lane;
         const int r = idx / PPR, q = idx % PPR;
-        uint4 t = make_uint4(0u, 0u, 0u, 0u);
-        if ((valid_mask >> r) & 1u) t = *reinterpret_cast<const uint4*>(base + (long long)r * ld * (int)sizeof(T) + s * SW + q * 16);
-        *reinterpret_cast<uint4*>(buf + r * STAGE_ROW_BYTES + q * 16) = t;
+        t[s][it] = make_uint4(0u, 0u, 0u, 0u);
+        if ((valid_mask >> r) & 1u)
+          t[s][it] = *reinterpret_cast<const uint4*>(base + (long long)r * ld * (int)sizeof(T) + s * SW + q * 16);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < PASSES; ++s) {
+#pragma unroll
+      for (int it = 0; it < PPR; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = idx / PPR, q = idx % PPR;
+        *reinterpret_cast<uint4*>(buf + r * STAGE_ROW_BYTES + q * 16) = t[s][it];
       }
       __syncwarp();
 #pragma unroll
@@ -197,21 +209,16 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long l
     for (int i = 0; i < NV; ++i) o[i] = gelu_fwd<FAST>(v[i]);
     io.template store<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, e.ldo, o, valid);
   } else if constexpr (KIND == EPI_GLU_BWD) {
-    // acc column c is d(h[c]); pre-activations of (value, gate) sit at aux[2c], aux[2c+1]
-    const TO* pa = reinterpret_cast<const TO*>(e.aux) + row * e.ldaux + 2 * col;
-    TO* po = reinterpret_cast<TO*>(e.out) + row * e.ldo + 2 * col;
+    // acc column c is d(h[c]); pre-activations of (value, gate) sit at aux[2c], aux[2c+1]; one 2*NV-wide load / store
+    float u[2 * NV];
+    io.template load<2 * NV>(reinterpret_cast<const TO*>(e.aux) + row * e.ldaux + 2 * col, e.ldaux, u, valid);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float u[NV], o[NV];
-      io.template load<NV>(pa + h * NV, e.ldaux, u, valid);
-#pragma unroll
-      for (int i = 0; i < NV; i += 2) {
-        const float dh = v[h * (NV / 2) + (i >> 1)];
-        o[i] = dh * gelu_fwd<FAST>(u[i + 1]);
-        o[i + 1] = dh * u[i] * gelu_bwd<FAST>(u[i + 1]);
-      }
-      io.template store<NV>(po + h * NV, e.ldo, o, valid);
+    for (int i = 0; i < NV; ++i) {
+      const float dh = v[i], val = u[2 * i], gate = u[2 * i + 1];
+      u[2 * i] = dh * gelu_fwd<FAST>(gate);
+      u[2 * i + 1] = dh * val * gelu_bwd<FAST>(gate);
     }
+    io.template store<2 * NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + 2 * col, e.ldo, u, valid);
   } else if constexpr (KIND == EPI_GELU_BWD) {
     float u[NV];
     io.template load<NV>(reinterpret_cast<const TO*>(e.aux) + row * e.ldaux + col, e.ldaux, u, valid);

@@ -367,11 +367,13 @@ class Engine:
                                       1.0 / global_batch, st), 'ce_fwd_bwd')
         self._backward_device()
 
-    def ln_bwd_res(self, dy, x, scale, mean, rstd, dscale, shift):
+    def ln_bwd_res(self, dy, x, scale, mean, rstd, dscale, shift, next_bias_grad=None):
+        """LN(+shift) backward into the residual-gradient stream; `next_bias_grad` (+= column sums of the updated dres) is
+        the bias gradient of the block that is differentiated next (its output bias sees exactly this dres)."""
         L.check(self.lib.progen_ln_shift_bwd(dy.data_ptr(), self.d, self.act_dt, x.data_ptr(), self.d, L.F32, scale.data_ptr(),
                                              mean.data_ptr(), rstd.data_ptr(), self.dres.data_ptr(),
-                                             self.dres_lp.data_ptr() if self.mp else 0, self.d, dscale.data_ptr(), self.T, self.d,
-                                             self.n, int(shift), 1, L.stream()), 'ln_bwd')
+                                             self.dres_lp.data_ptr() if self.mp else 0, self.d, dscale.data_ptr(),
+                                             L.ptr(next_bias_grad), self.T, self.d, self.n, int(shift), 1, L.stream()), 'ln_bwd')
 
     def _backward_device(self):
         lib, st = self.lib, L.stream()
@@ -383,14 +385,15 @@ class Engine:
         self.wgrad_gemm(self.yf, d, self.dlogits, self.V, self.G(hw, 'w'))
         self.dgrad_gemm(self.dlogits, self.V, self.W(hw, 'w'), d, self.dy)
         self.dres.zero_()
-        self.ln_bwd_res(self.dy, self.X[-1], self.Pf(hl, 'scale'), self.meanf, self.rstdf, self.G(hl, 'scale'), False)
+        nl = len(self.kinds)
+        self.ln_bwd_res(self.dy, self.X[-1], self.Pf(hl, 'scale'), self.meanf, self.rstdf, self.G(hl, 'scale'), False,
+                        next_bias_grad=self.G(P + f'ff{nl - 1}/~/linear_1', 'b'))
         for i in reversed(range(len(self.kinds))):
             kind, s = self.kinds[i], self.lay[i]
             a, f = P + f'attn{i}/~/', P + f'ff{i}/~/'
             x0, x1 = self.X[2 * i], self.X[2 * i + 1]
             dres_lp = self.dres_lp
-            # ---- FeedForward backward
-            self.colsum(self.dres, d, self.G(f + 'linear_1', 'b'))
+            # ---- FeedForward backward (d(proj_out bias) = colsum(dres) was produced by the previous LN backward)
             if kind == 'sgu':
                 half = hid // 2
                 g = f + 'sgu'
@@ -415,7 +418,7 @@ class Engine:
                 L.check(lib.progen_ln_shift_bwd(self.dgn.data_ptr(), half, self.act_dt, gate.data_ptr(), hid, self.act_dt,
                                                 self.Pf(g + '/~/layer_norm', 'scale').data_ptr(), s['mean3'].data_ptr(),
                                                 s['rstd3'].data_ptr(), 0, da[:, half:].data_ptr(), hid,
-                                                self.G(g + '/~/layer_norm', 'scale').data_ptr(), T, half, n, 0, 0, st), 'ln_bwd_sgu')
+                                                self.G(g + '/~/layer_norm', 'scale').data_ptr(), 0, T, half, n, 0, 0, st), 'ln_bwd_sgu')
                 L.check(lib.progen_gelu_bwd(da.data_ptr(), s['u'].data_ptr(), self.act_dt, T * hid, st), 'gelu_bwd')
                 du, n_in = da, hid
             elif kind == 'glu':
@@ -430,9 +433,9 @@ class Engine:
             self.colsum(du, n_in, self.G(f + 'linear', 'b'))
             self.wgrad_gemm(s['y2'], d, du, n_in, self.G(f + 'linear', 'w'))
             self.dgrad_gemm(du, n_in, self.W(f + 'linear', 'w'), d, self.dy)
-            self.ln_bwd_res(self.dy, x1, self.Pf(f + 'layer_norm', 'scale'), s['mean2'], s['rstd2'], self.G(f + 'layer_norm', 'scale'), shift)
+            self.ln_bwd_res(self.dy, x1, self.Pf(f + 'layer_norm', 'scale'), s['mean2'], s['rstd2'], self.G(f + 'layer_norm', 'scale'), shift,
+                            next_bias_grad=self.G(a + 'linear_1', 'b'))
             # ---- LocalAttention backward
-            self.colsum(self.dres, d, self.G(a + 'linear_1', 'b'))
             self.wgrad_gemm(s['att'], I, dres_lp, d, self.G(a + 'linear_1', 'w'))
             self.dgrad_gemm(dres_lp, d, self.W(a + 'linear_1', 'w'), I, self.datt)
             self.attn_bwd(s['qkv'], s['att'], self.datt, s['lse'], self.dqkv)
@@ -441,6 +444,7 @@ class Engine:
                                               self.rot_cos.data_ptr(), T, 3 * I, n, self.dh, st), 'rotary_bwd')
             self.wgrad_gemm(s['y1'], d, self.dqkv, 3 * I, self.G(a + 'linear', 'w'))
             self.dgrad_gemm(self.dqkv, 3 * I, self.W(a + 'linear', 'w'), d, self.dy)
-            self.ln_bwd_res(self.dy, x0, self.Pf(a + 'layer_norm', 'scale'), s['mean1'], s['rstd1'], self.G(a + 'layer_norm', 'scale'), shift)
+            self.ln_bwd_res(self.dy, x0, self.Pf(a + 'layer_norm', 'scale'), s['mean1'], s['rstd1'], self.G(a + 'layer_norm', 'scale'), shift,
+                            next_bias_grad=self.G(P + f'ff{i - 1}/~/linear_1', 'b') if i > 0 else None)
         L.check(lib.progen_embed_bwd(self.tok.data_ptr(), self.dres.data_ptr(), self.G(P + 'embed', 'embeddings').data_ptr(),
                                      T, d, self.V, st), 'embed_bwd')

@@ -49,7 +49,7 @@ PROTOTYPES = {
     'progen_embed_fwd': [_P, _P, _P, _LL, _I, _I, _P],
     'progen_embed_bwd': [_P, _P, _P, _LL, _I, _I, _P],
     'progen_ln_shift_fwd': [_P, _LL, _I, _P, _P, _LL, _I, _P, _P, _LL, _I, _I, _I, _P],
-    'progen_ln_shift_bwd': [_P, _LL, _I, _P, _LL, _I, _P, _P, _P, _P, _P, _LL, _P, _LL, _I, _I, _I, _I, _P],
+    'progen_ln_shift_bwd': [_P, _LL, _I, _P, _LL, _I, _P, _P, _P, _P, _P, _LL, _P, _P, _LL, _I, _I, _I, _I, _P],
     'progen_colsum': [_P, _LL, _I, _P, _LL, _I, _P],
     'progen_ce_fwd_bwd': [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     'progen_rotary_bwd': [_P, _LL, _I, _P, _P, _LL, _I, _I, _I, _P],

@@ -15,8 +15,9 @@ from progen_b200.utils import sample
 @click.option('--checkpoint_path', default='./ckpts')
 @click.option('--prime', default='')
 @click.option('--greedy', default=False, is_flag=True)
-@click.option('--mixed_precision', default=False, is_flag=True)
-def main(seed, checkpoint_path, prime, greedy, mixed_precision):
+@click.option('--mixed_precision', default=False, is_flag=True, help='bf16 weights in the decode kernels')
+@click.option('--no_kv_cache', default=False, is_flag=True, help="reference-style loop: full re-forward per token")
+def main(seed, checkpoint_path, prime, greedy, mixed_precision, no_kv_cache):
     _, get_last_checkpoint, _ = get_checkpoint_fns(checkpoint_path)
     last_checkpoint = get_last_checkpoint()
     if last_checkpoint is None:
@@ -32,7 +33,14 @@ def main(seed, checkpoint_path, prime, greedy, mixed_precision):
     prime_tokens = encode_tokens(prime)
     prime_length = len(prime_tokens) + 1
     prime_tensor = np.array(prime_tokens, dtype=np.uint16)
-    sampled = sample(seed, model.apply, params, prime_tensor, seq_len, top_k=25, add_bos=True, greedy=greedy)
+    if no_kv_cache:
+        sampled = sample(seed, model.apply, params, prime_tensor, seq_len, top_k=25, add_bos=True, greedy=greedy)
+    else:
+        import torch
+        from progen_b200.decode import Decoder
+        dec = Decoder(model.config, params, weights_dtype=torch.bfloat16 if mixed_precision else torch.float32)
+        sampled, steps, secs = dec.sample(prime_tensor, top_k=25, add_bos=True, greedy=greedy, seed=seed)
+        print(f'decoded {steps} tokens at {steps / max(secs, 1e-9):.0f} tokens/s (device time, KV-cached)')
     print('\n', prime, '\n', '*' * 40, '\n', decode_tokens(sampled[prime_length:]))
 
 

@@ -57,13 +57,15 @@ def test_ln_shift_fwd_bwd(act, shift, d):
     dres = dres0.clone()
     dres_lp = torch.empty(T, d, device=dev, dtype=act)
     dscale = torch.zeros(d, device=dev)
+    csum = torch.zeros(d, device=dev)
     L.check(L.load().progen_ln_shift_bwd(dy.data_ptr(), d, L.dt(dy), x.data_ptr(), d, L.F32, scale.data_ptr(), mean.data_ptr(),
-                                         rstd.data_ptr(), dres.data_ptr(), dres_lp.data_ptr(), d, dscale.data_ptr(), T, d, n,
-                                         shift, 1, L.stream()))
+                                         rstd.data_ptr(), dres.data_ptr(), dres_lp.data_ptr(), d, dscale.data_ptr(), csum.data_ptr(),
+                                         T, d, n, shift, 1, L.stream()))
     ref.backward(dy.double())
     assert (dres.double() - (dres0.double() + xd.grad)).abs().max().item() < 1e-4 * max(1.0, xd.grad.abs().max().item())
     assert (dscale.double() - sd.grad).abs().max().item() < 1e-3 * max(1.0, sd.grad.abs().max().item())
     assert (dres_lp.double() - dres.double()).abs().max().item() <= (1e-6 if act == torch.float32 else 0.05)
+    assert (csum.double() - dres.double().sum(0)).abs().max().item() < 1e-3 * max(1.0, dres.double().sum(0).abs().max().item())
 
 
 def test_ln_strided_act_input():
@@ -88,7 +90,7 @@ def test_ln_strided_act_input():
     da = torch.zeros(T, 2 * C, device=dev, dtype=torch.bfloat16)
     dscale = torch.zeros(C, device=dev)
     L.check(L.load().progen_ln_shift_bwd(dy.data_ptr(), C, L.BF16, gate.data_ptr(), 2 * C, L.BF16, scale.data_ptr(),
-                                         mean.data_ptr(), rstd.data_ptr(), 0, da[:, C:].data_ptr(), 2 * C, dscale.data_ptr(),
+                                         mean.data_ptr(), rstd.data_ptr(), 0, da[:, C:].data_ptr(), 2 * C, dscale.data_ptr(), 0,
                                          T, C, T, 0, 0, L.stream()))
     ref.backward(dy.double())
     assert (da[:, C:].double() - xd.grad).abs().max().item() < 2e-2 * xd.grad.abs().max().item()

@@ -16,7 +16,7 @@ import torch
 from progen_b200 import ProGen
 from progen_b200 import parallel as PAR
 from progen_b200.checkpoint import get_checkpoint_fns
-from progen_b200.data import decode_tokens, iterator_from_sequences, synthetic_iterator
+from progen_b200.data import decode_tokens, iterator_from_sequences, iterator_from_tfrecords_folder, synthetic_iterator
 from progen_b200.utils import sample, confirm, exists
 
 
@@ -87,8 +87,13 @@ def main(seed, batch_size, grad_accum_every, learning_rate, weight_decay, data_p
         train_dataset = iterator_from_sequences(lines[:cut], seq_len, batch_size, skip=start_seq_index, loop=False)
         valid_dataset = iterator_from_sequences(lines[cut:] or lines[:1], seq_len, batch_size, loop=True)
     else:
-        raise click.UsageError('TFRecord reading needs tensorflow, which is outside the B200 hot path: use --synthetic or '
-                               '--text_file (see DESIGN.md, out of scope)')
+        # the reference's data layout (train.py:154-170): gzip TFRecords under --data_path, read without tensorflow
+        total_train_seqs, get_train_dataset = iterator_from_tfrecords_folder(data_path, data_type='train')
+        total_valid_seqs, get_valid_dataset = iterator_from_tfrecords_folder(data_path, data_type='valid')
+        assert total_train_seqs > 0, 'no protein sequences found for training'
+        assert total_valid_seqs > 0, 'no protein sequences found for validation'
+        train_dataset = get_train_dataset(seq_len=seq_len, batch_size=batch_size, skip=start_seq_index)
+        valid_dataset = get_valid_dataset(seq_len=seq_len, batch_size=batch_size, loop=True)
     if rank == 0:
         print(f'params: {num_params}')
         print(f'sequence length: {seq_len}')
