@@ -30,6 +30,10 @@ CONFIGS = {
     'cfg3': dict(kwargs=dict(num_tokens=256, dim=1024, seq_len=2048, depth=24, heads=16, dim_head=64, window_size=512,
                              global_mlp_depth=2, ff_glu=True), batch=8,
                  name='ProGen dim=1024 depth=24 heads=16 seq_len=2048 window=512 gmlp=2 bf16 - training step (BASELINE configs[2])'),
+    # BASELINE.json configs[3]: HBM-bandwidth stress (heads unspecified => constructor default 8 x 64, so inner 512 != dim)
+    'cfg4': dict(kwargs=dict(num_tokens=256, dim=1536, seq_len=4096, depth=36, heads=8, dim_head=64, window_size=256,
+                             global_mlp_depth=2, ff_glu=True), batch=4,
+                 name='ProGen dim=1536 depth=36 seq_len=4096 window=256 ff_glu bf16 - training step (BASELINE configs[3])'),
     'tiny': dict(kwargs=dict(num_tokens=256, dim=128, seq_len=128, depth=2, heads=2, dim_head=64, window_size=64,
                              global_mlp_depth=1, ff_glu=True), batch=4, name='tiny smoke configuration (not a bench line)'),
 }
@@ -221,6 +225,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'             # the version banner goes to stdout; keep it to the single JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
     L.require_device()

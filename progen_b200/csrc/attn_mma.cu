@@ -259,9 +259,10 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
 // ================================================================================================ dQ
 // dQ = scale * sum_tiles (P o (dO V^T - delta)) K,  P = exp(scale * Q K^T - lse)
 template <int BQ>
-__global__ void __launch_bounds__(BQ * 2) attn_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                                 const float* __restrict__ lse, const float* __restrict__ delta,
-                                                                 bf16* __restrict__ dqkv, const Dims dm) {
+__global__ void __launch_bounds__(BQ * 2) attn_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+                                                                 const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                                                 float* __restrict__ delta, bf16* __restrict__ dqkv,
+                                                                 const Dims dm) {
   constexpr int THREADS = BQ * 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(BQ * 2) attn_bwd_dq_mma_kernel(const bf16* __r
   for (int r = 0; r < 2; ++r) {
     const long long t = seq_row0 + q0 + warp * 16 + g + 8 * r;
     L2[r] = lse[t * dm.h + hh] * LOG2E;
-    Dl[r] = delta[t * dm.h + hh];
+    Dl[r] = 0.f;
   }
   float dq[8][4];
   zero_acc(dq);
@@ -318,6 +319,28 @@ __global__ void __launch_bounds__(BQ * 2) attn_bwd_dq_mma_kernel(const bf16* __r
     if (kt == 0) {
       load_a_frags(qa, sQ, warp * 16, lane);
       load_a_frags(doa, sdO, warp * 16, lane);
+      // delta = rowsum(dO o O), fused here (was a separate pass): this thread's dO fragment elements against the same
+      // elements of O read straight from global; the quad completes the row.  Also published for the dK/dV kernel.
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const long long t = seq_row0 + q0 + warp * 16 + g + 8 * r;
+            const uint32_t ov = *reinterpret_cast<const uint32_t*>(out + t * I + hh * DH + 16 * kk + 8 * hf + 2 * t4);
+            const uint32_t dv = doa[kk][2 * hf + r];
+            const float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov));
+            const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dv));
+            Dl[r] += fo.x * fd.x + fo.y * fd.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        Dl[r] = quad_sum(Dl[r]);
+        if (t4 == 0) delta[(seq_row0 + q0 + warp * 16 + g + 8 * r) * dm.h + hh] = Dl[r];
+      }
     }
     const int c0 = (kt - nprev) * BKV;
     const bool own = kt >= nprev;
@@ -500,12 +523,12 @@ template <int BQ> int launch_fwd_t(const bf16* qkv, bf16* out, float* lse, const
   PG_LAUNCH_CHECK();
   return PROGEN_OK;
 }
-template <int BQ> int launch_dq_t(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv,
+template <int BQ> int launch_dq_t(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                                   const Dims& dm, int B, cudaStream_t s) {
   const int smem = 2 * BQ * 128 + 4 * BKV * 128;
   static bool once = false;
   if (!once) { int rc = set_smem(attn_bwd_dq_mma_kernel<BQ>, smem); if (rc) return rc; once = true; }
-  attn_bwd_dq_mma_kernel<BQ><<<dim3(dm.n / BQ, dm.h, B), BQ * 2, smem, s>>>(qkv, dout, lse, delta, dqkv, dm);
+  attn_bwd_dq_mma_kernel<BQ><<<dim3(dm.n / BQ, dm.h, B), BQ * 2, smem, s>>>(qkv, out, dout, lse, delta, dqkv, dm);
   PG_LAUNCH_CHECK();
   return PROGEN_OK;
 }
@@ -542,12 +565,10 @@ int progen_local_attn_bwd(const void* qkv, const void* out, const void* dout, co
   PG_CHECK_ARG(B > 0 && heads > 0 && dim_head == DH && window % 64 == 0 && seq_len % window == 0);
   Dims dm{seq_len, window, heads, rot_sin, rot_cos};
   cudaStream_t s = (cudaStream_t)stream;
-  const long long rows = (long long)B * seq_len * heads;
-  attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, rows);
-  PG_LAUNCH_CHECK();
   const TileChoice tc = tile_choice(window);
-  int rc = tc.dq == 128 ? launch_dq_t<128>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s)
-                        : launch_dq_t<64>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s);
+  // the dQ kernel also produces delta = rowsum(dO o O) for the dK/dV kernel that follows it on the same stream
+  int rc = tc.dq == 128 ? launch_dq_t<128>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s)
+                        : launch_dq_t<64>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s);
   if (rc) return rc;
   return tc.dkv == 128 ? launch_dkv_t<128>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s)
                        : launch_dkv_t<64>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, B, s);

@@ -105,6 +105,17 @@ template <bool FAST> __device__ __forceinline__ float gelu_bwd(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
 }
 
+// gelu(x) and gelu'(x) from ONE tanh (the GLU backward epilogue needs both for the same argument)
+template <bool FAST> __device__ __forceinline__ void gelu_fwd_bwd(float x, float& f, float& df) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float u = k0 * (x + k1 * x * x2);
+  const float t = FAST ? tanh_fast(u) : tanhf(u);
+  const float h = 0.5f * (1.0f + t);
+  f = x * h;
+  df = h + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
+}
+
 // vector load/store of NV consecutive elements (NV * sizeof(T) must be a multiple of 16 bytes, pointer aligned)
 template <int NV> __device__ __forceinline__ void load_vec(const float* p, float (&v)[NV]) {
 #pragma unroll

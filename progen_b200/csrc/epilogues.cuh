@@ -158,8 +158,15 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long l
       // the NV columns sit inside one head: NV/2 consecutive (sin, cos) entries, 16-byte vector loads
       const int j0 = (col % e.dim_head) >> 1;
       float s[NV / 2], c[NV / 2];
-      load_vec<NV / 2>(sp + j0, s);
-      load_vec<NV / 2>(cp + j0, c);
+      if constexpr (NV >= 32) {
+        // consecutive rows are consecutive positions (a warp's 32 rows never straddle a sequence: seq_len % 32 == 0
+        // is checked by the launcher), so the table slices form a [32 x NV/2] block: coalesced staged loads
+        io.template load<NV / 2>(sp + j0, half, s, true);
+        io.template load<NV / 2>(cp + j0, half, c, true);
+      } else {
+        load_vec<NV / 2>(sp + j0, s);
+        load_vec<NV / 2>(cp + j0, c);
+      }
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
         o[i] = v[i] * c[i >> 1] - v[i + 1] * s[i >> 1];
@@ -215,8 +222,10 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long l
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float dh = v[i], val = u[2 * i], gate = u[2 * i + 1];
-      u[2 * i] = dh * gelu_fwd<FAST>(gate);
-      u[2 * i + 1] = dh * val * gelu_bwd<FAST>(gate);
+      float gf, gd;
+      gelu_fwd_bwd<FAST>(gate, gf, gd);
+      u[2 * i] = dh * gf;
+      u[2 * i + 1] = dh * val * gd;
     }
     io.template store<2 * NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + 2 * col, e.ldo, u, valid);
   } else if constexpr (KIND == EPI_GELU_BWD) {

@@ -290,6 +290,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const bool has_k = ti.kb_end > ti.kb_begin;
       const bool valid = m < g.M;
       io.valid_mask = __ballot_sync(0xffffffffu, valid);
+      // EPI_ROTARY, dim_head 64: the 32 (sin, cos) pairs of this row's position serve every head of the tile; fetch them
+      // once per tile (two coalesced staged loads) instead of once per 32-column chunk
+      float rs[KIND == EPI_ROTARY ? 32 : 1], rc[KIND == EPI_ROTARY ? 32 : 1];
+      bool rot_cached = false;
+      if constexpr (KIND == EPI_ROTARY) {
+        if (g.epi.dim_head == 64) {
+          const long long pos = row % g.epi.seq_len;
+          io.template load<32>(g.epi.rot_sin + pos * 32, 32, rs, true);
+          io.template load<32>(g.epi.rot_cos + pos * 32, 32, rc, true);
+          rot_cached = true;
+        }
+      }
 #pragma unroll 1
       for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int col = ti.n0 + c * 32;
@@ -299,6 +311,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (!has_k) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if constexpr (KIND == EPI_ROTARY) {
+          if (rot_cached) {
+            float o[32];
+            if ((col & 32) == 0) {                      // first / second half of the head: pairs 0..15 / 16..31
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                o[i] = v[i] * rc[i >> 1] - v[i + 1] * rs[i >> 1];
+                o[i + 1] = v[i + 1] * rc[i >> 1] + v[i] * rs[i >> 1];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                o[i] = v[i] * rc[16 + (i >> 1)] - v[i + 1] * rs[16 + (i >> 1)];
+                o[i + 1] = v[i + 1] * rc[16 + (i >> 1)] + v[i] * rs[16 + (i >> 1)];
+              }
+            }
+            io.template store<32>(reinterpret_cast<TO*>(g.epi.out) + row * g.epi.ldo + col, g.epi.ldo, o, valid);
+            continue;
+          }
         }
         epi_apply<KIND, TO, 32>(g.epi, io, row, col, v, valid);
       }
@@ -413,6 +445,7 @@ int gemm_tc_launch(const GemmArgs& a, cudaStream_t stream) {
   PG_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0);    // 16-byte global strides for TMA
   PG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
   PG_CHECK_ARG(!(a.split_k > 1 && a.causal));
+  if (a.epi_kind == EPI_ROTARY) PG_CHECK_ARG(a.epi.seq_len % 32 == 0);   // staged sin/cos loads: a warp's rows stay in one sequence
   PG_CHECK_ARG(!(a.split_k > 1 || a.batch_reduce) || (a.epi_kind == EPI_ACCUM && a.epi.atomic));
   if (a.batch > 1 && a.a_batch_rows > 0 && !a.a_mn_major) PG_CHECK_ARG(a.M % BM == 0 || a.batch_reduce || true);
 

@@ -129,7 +129,14 @@ class Engine:
         self.rot_cos = torch.tensor(np.cos(ang), **f32).contiguous()
         self.B = 0
         self.loaded_token = None
+        self.on_layer_grads = None        # optional callback(layer_index) fired when a layer's weight gradients are final
         self.lib = L.load()
+
+    def layer_grad_range(self, i):
+        """[start, stop) of layer i's ndim>1 parameters inside the flat buffers (contiguous by construction)."""
+        pre = (P + f'attn{i}/~/', P + f'ff{i}/~/')
+        segs = [s for s in self.specs if s.decay and s.module.startswith(pre)]
+        return min(s.offset for s in segs), max(s.offset + (s.size + ALIGN - 1) // ALIGN * ALIGN for s in segs)
 
     # ------------------------------------------------------------------------------------------ parameters
     def seg(self, buf, module, name):
@@ -446,5 +453,9 @@ class Engine:
             self.dgrad_gemm(self.dqkv, 3 * I, self.W(a + 'linear', 'w'), d, self.dy)
             self.ln_bwd_res(self.dy, x0, self.Pf(a + 'layer_norm', 'scale'), s['mean1'], s['rstd1'], self.G(a + 'layer_norm', 'scale'), shift,
                             next_bias_grad=self.G(P + f'ff{i - 1}/~/linear_1', 'b') if i > 0 else None)
+            if self.on_layer_grads is not None:
+                # every weight-matrix gradient of layer i is final: the DDP trainer starts its all-reduce here so the
+                # transfer overlaps the backward pass of layers i-1 .. 0
+                self.on_layer_grads(i)
         L.check(lib.progen_embed_bwd(self.tok.data_ptr(), self.dres.data_ptr(), self.G(P + 'embed', 'embeddings').data_ptr(),
                                      T, d, self.V, st), 'embed_bwd')

@@ -24,6 +24,10 @@ class Trainer:
         self.ws = torch.empty(L.load().progen_optim_workspace_floats(), device=self.eng.dev)
         self.gnorm_sq = torch.zeros(1, device=self.eng.dev)
         self.rank, self.world = PAR.world() if data_parallel else (0, 1)
+        self._works, self._done = [], []
+        if self.world > 1:
+            # overlap: a layer's weight gradients are all-reduced (async, NCCL's stream) as soon as its backward is done
+            self.eng.on_layer_grads = self._reduce_layer
         if optim_state is not None:
             self.load_optim_state(optim_state)
 
@@ -39,10 +43,31 @@ class Trainer:
         self.eng.step_device(global_batch or self.eng.B * self.world)
         return self._update(sync_loss)
 
+    def _reduce_layer(self, i):
+        import torch.distributed as dist
+        a, b = self.eng.layer_grad_range(i)
+        self._works.append(dist.all_reduce(self.eng.grads[a:b], op=dist.ReduceOp.SUM, async_op=True))
+        self._done.append((a, b))
+
+    def _finish_allreduce(self):
+        """everything the per-layer reductions did not cover: embedding (final only at the very end of backward), head,
+        and the small ndim<=1 section; then wait for the overlapped ones"""
+        eng = self.eng
+        lo = min((a for a, _ in self._done), default=eng.n_params_padded)
+        hi = max((b for _, b in self._done), default=eng.n_params_padded)
+        if self._done:
+            PAR.allreduce_sum_(eng.grads[:lo])
+            PAR.allreduce_sum_(eng.grads[hi:])
+        else:
+            PAR.allreduce_sum_(eng.grads)
+        for w in self._works:
+            w.wait()
+        self._works, self._done = [], []
+
     def _update(self, sync_loss):
         eng, lib, st = self.eng, L.load(), L.stream()
         if self.world > 1:
-            PAR.allreduce_sum_(eng.grads)
+            self._finish_allreduce()
             if sync_loss:
                 PAR.allreduce_scalar_(eng.loss)
         self.count += 1

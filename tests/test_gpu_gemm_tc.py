@@ -71,3 +71,13 @@ def test_tc_batched_causal_and_reduce():
            epi=L.EPI_ACCUM, batch=B, a_batch_rows=n, b_batch_rows=n, batch_reduce=True, atomic=True, tril=True, tril_rows=n)
     ref = torch.tril(torch.einsum('bmc,bkc->mk', G.view(B, n, C).double(), X.view(B, n, C).double()))
     assert (dW.double() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+def test_tc_gemm_rotary_dim_head_64_cached_tables():
+    """dim_head 64 takes the per-tile cached sin/cos path of the epilogue; several sequences per tile column block."""
+    from progen_b200 import lib as L
+    from gemm_cases import run_case
+    err, scale = run_case(L.BACKEND_TC, torch.bfloat16, 512, 384, 128, False, True, L.EPI_ROTARY, seed=11, seq_len=128, dim_head=64)
+    assert err <= BF16_OUT_TOL * max(1.0, scale), (err, scale)
+    err, scale = run_case(L.BACKEND_TC, torch.bfloat16, 200, 256, 64, False, True, L.EPI_ROTARY, seed=12, seq_len=64, dim_head=64)
+    assert err <= BF16_OUT_TOL * max(1.0, scale), (err, scale)
