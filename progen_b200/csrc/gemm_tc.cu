@@ -437,6 +437,12 @@ int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDe
 
 }  // namespace
 
+// shared with the other tensor-core kernels (attn_tc.cu)
+int pg_tensor_map_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_elems, uint32_t box_inner,
+                          uint32_t box_outer, CUtensorMap* out) {
+  return get_tensor_map(ptr, inner, outer, row_stride_elems, box_inner, box_outer, out);
+}
+
 int gemm_tc_launch(const GemmArgs& a, cudaStream_t stream) {
   PG_CHECK_ARG(a.in_dtype == PG_BF16);
   PG_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0 && a.batch >= 1 && a.split_k >= 1);

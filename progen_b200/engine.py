@@ -96,6 +96,10 @@ class Engine:
         self.kinds = layer_kinds(cfg['depth'], cfg['global_mlp_depth'], cfg['ff_glu'])
         # tensor-core attention kernel needs bf16, dim_head 64 and 64-aligned windows; other shapes use the CUDA-core kernel
         self.attn_tc = self.mp and cfg['dim_head'] == 64 and cfg['window_size'] % 64 == 0
+        import os
+        self.attn_fwd_kind = os.environ.get('PROGEN_ATTN_FWD', 'mma')
+        if self.attn_fwd_kind == 'tcgen05' and cfg['window_size'] % 128 != 0:
+            self.attn_fwd_kind = 'mma'
         d, n, w = cfg['dim'], cfg['seq_len'], cfg['window_size']
         self.d, self.n, self.w, self.V = d, n, w, cfg['num_tokens']
         self.h, self.dh = cfg['heads'], cfg['dim_head']
@@ -332,6 +336,12 @@ class Engine:
 
     def attn_fwd(self, qkv, out, lse):
         if self.attn_tc:
+            # two tensor-core forwards: `mma` (mma.sync flash kernel, currently the faster one) and `tcgen05` (TMA + tcgen05.mma +
+            # TMEM, attn_tc.cu; needs window % 128 == 0).  PROGEN_ATTN_FWD selects; default = mma.
+            if self.attn_fwd_kind == 'tcgen05':
+                L.check(self.lib.progen_local_attn_fwd_tc(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), self.B, self.n, self.w,
+                                                          self.h, self.dh, L.stream()), 'local_attn_fwd_tc')
+                return
             L.check(self.lib.progen_local_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), self.B, self.n, self.w, self.h,
                                                    self.dh, L.stream()), 'local_attn_fwd')
             return

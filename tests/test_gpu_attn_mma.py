@@ -60,3 +60,30 @@ def test_local_attn_mma_fwd_bwd(cfg):
     exp1 = ref2[..., 1] * c_ - ref2[..., 0] * s_
     expect = torch.stack((exp0, exp1), dim=-1).flatten(-2)
     assert (fused.double() - expect).abs().max().item() < 3e-2 * max(1.0, expect.abs().max().item())
+
+
+@pytest.mark.parametrize('cfg', [(2, 256, 128, 2), (1, 512, 256, 3), (1, 1024, 256, 8), (3, 128, 128, 1), (2, 1024, 512, 2),
+                                 (5, 512, 256, 8)])
+def test_local_attn_tcgen05_fwd(cfg):
+    """tcgen05 / TMEM forward kernel (attn_tc.cu) vs the float64 reference and the mma.sync kernel's log-sum-exp."""
+    from progen_b200 import lib as L
+    L.require_device()
+    B, n, w, h = cfg
+    dh = 64
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(7 * n + w)
+    T, I = B * n, h * dh
+    qkv = (torch.randn(T, 3 * I, generator=g, device=dev) * 1.5).bfloat16()
+    out = torch.full((T, I), float('nan'), device=dev, dtype=torch.bfloat16)
+    lse = torch.full((T, h), float('nan'), device=dev)
+    L.check(L.load().progen_local_attn_fwd_tc(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, n, w, h, dh, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    ref = attn_ref(qkv.double(), B, n, w, h, dh)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-2, err
+    out2 = torch.empty_like(out)
+    lse2 = torch.empty_like(lse)
+    L.check(L.load().progen_local_attn_fwd(qkv.data_ptr(), out2.data_ptr(), lse2.data_ptr(), B, n, w, h, dh, L.stream()))
+    assert (lse - lse2).abs().max().item() < 2e-3
+    assert (out.float() - out2.float()).abs().max().item() < 2e-2
