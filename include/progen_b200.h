@@ -121,6 +121,11 @@ int progen_local_attn_bwd(const void* qkv, const void* out, const void* dout, co
 int progen_local_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int seq_len, int window, int heads, int dim_head,
                              void* stream);
 
+/* tcgen05 backward (dQ kernel + dK/dV kernel, no atomics; delta produced by the dQ kernel); window % 128 == 0 */
+int progen_local_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                             const float* rot_sin, const float* rot_cos, int B, int seq_len, int window, int heads, int dim_head,
+                             void* stream);
+
 /* SGU gating — progen.py:182-184: out = xs * (Gp + spatial_biases[m]) and its backward (dxs, dGp, dbias) */
 int progen_sgu_gate_fwd(const void* xs, long long ldx, const void* gp, long long ldg, const float* bias, void* out,
                         long long ldo, int dtype, long long T, int C, int seq_len, void* stream);
