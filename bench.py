@@ -266,7 +266,10 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clocks = sampler.stop() if sampler else None
-    final_loss = float(eng.loss.item())
+    loss_t = eng.loss.clone()
+    if world > 1:
+        dist.all_reduce(loss_t)                        # per-rank losses are pre-scaled by 1/global_batch: the sum is the mean
+    final_loss = float(loss_t.item())
 
     # ---------------- end-to-end leg: public API with HOST (pinned) buffers, H2D + loss D2H inside the timed region
     for i in range(min(2, args.warmup)):

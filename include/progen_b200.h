@@ -167,8 +167,8 @@ typedef struct progen_decode_layer_t {
   const float* sgu_proj_b;
   float* kcache;               /* [n, inner] rotated keys */
   float* vcache;               /* [n, inner] rotated values */
-  float* shift1;               /* [d/2] previous position's LN half (attention block) */
-  float* shift2;               /* [d/2] previous position's LN half (feed-forward block) */
+  float* shift1;               /* [2][d/2] previous position's LN half (attention block), indexed by position parity */
+  float* shift2;               /* [2][d/2] previous position's LN half (feed-forward block) */
   float* gn_hist;              /* [n, hid/2] normalised gate history (gMLP layers) */
 } progen_decode_layer_t;
 

@@ -28,6 +28,10 @@ struct GemvArgs {
   // DE_ROTARY_CACHE
   float* kcache; float* vcache; const float* rot_sin; const float* rot_cos; int inner; int dim_head;
   const int* pos;
+  // fused prologue: x <- shift_tokens(LayerNorm(x) * ln_scale) (progen.py:74-77 / 132-135 / 220); every block recomputes the
+  // row statistics (K floats), block 0 updates the token-shift cache.  ln_prev is double-buffered by position parity:
+  // read [pos & 1], write [(pos + 1) & 1], so no block races with block 0's update.
+  const float* ln_scale; float* ln_prev; int ln_shift;
 };
 
 template <typename TW> __device__ __forceinline__ float dot_row(const TW* __restrict__ w, const float* __restrict__ xs, int K, int lane);
@@ -54,9 +58,43 @@ template <> __device__ __forceinline__ float dot_row<bf16>(const bf16* __restric
 template <typename TW, int EPI>
 __global__ void __launch_bounds__(GV_THREADS) decode_gemv_kernel(const GemvArgs a) {
   extern __shared__ float xs[];
-  for (int k = threadIdx.x; k < a.K; k += GV_THREADS) xs[k] = a.x[k];
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (a.ln_scale) {
+    __shared__ float red[GV_WARPS];
+    __shared__ float stat[2];
+    float s = 0.f;
+    for (int k = threadIdx.x; k < a.K; k += GV_THREADS) { const float v = a.x[k]; xs[k] = v; s += v; }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < GV_WARPS; ++i) t += red[i]; stat[0] = t / a.K; }
+    __syncthreads();
+    const float mean = stat[0];
+    float q = 0.f;
+    for (int k = threadIdx.x; k < a.K; k += GV_THREADS) { const float u = xs[k] - mean; q += u * u; }
+    q = warp_sum(q);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < GV_WARPS; ++i) t += red[i]; stat[1] = rsqrtf(t / a.K + 1e-5f); }
+    __syncthreads();
+    const float rstd = stat[1];
+    const int half = a.K >> 1;
+    const int p = a.ln_shift ? *a.pos : 0;
+    const float* prev_rd = a.ln_prev + (p & 1) * half;
+    float* prev_wr = a.ln_prev + ((p + 1) & 1) * half;
+    for (int k = threadIdx.x; k < a.K; k += GV_THREADS) {
+      const float v = (xs[k] - mean) * rstd * a.ln_scale[k];
+      if (a.ln_shift && k < half) {
+        xs[k] = prev_rd[k];
+        if (blockIdx.x == 0) prev_wr[k] = v;
+      } else {
+        xs[k] = v;
+      }
+    }
+  } else {
+    for (int k = threadIdx.x; k < a.K; k += GV_THREADS) xs[k] = a.x[k];
+  }
+  __syncthreads();
   const int pair = blockIdx.x * GV_WARPS + warp;
   const TW* W = reinterpret_cast<const TW*>(a.wt);
   int r0, r1;
@@ -272,10 +310,9 @@ int progen_decode_step(const progen_decode_t* m, int do_sample, void* stream) {
   for (int i = 0; i < m->depth; ++i) {
     const progen_decode_layer_t& L = m->layers[i];
     // ---- LocalAttention
-    decode_ln_kernel<<<1, 256, 0, s>>>(m->x, L.ln1_scale, L.shift1, m->y, d, m->shift_tokens);
-    PG_LAUNCH_CHECK();
     GemvArgs a{};
-    a.wt = L.wqkv_t; a.x = m->y; a.bias = nullptr; a.out = m->q; a.N = 3 * I; a.K = d;
+    a.wt = L.wqkv_t; a.x = m->x; a.bias = nullptr; a.out = m->q; a.N = 3 * I; a.K = d;
+    a.ln_scale = L.ln1_scale; a.ln_prev = L.shift1; a.ln_shift = m->shift_tokens;       // LN + token shift fused in the prologue
     a.kcache = L.kcache; a.vcache = L.vcache; a.rot_sin = m->rot_sin; a.rot_cos = m->rot_cos; a.inner = I; a.dim_head = m->dim_head;
     a.pos = m->pos;
     int rc = gemv_dispatch(m->wdtype, DE_ROTARY_CACHE, a, s);
@@ -288,10 +325,9 @@ int progen_decode_step(const progen_decode_t* m, int do_sample, void* stream) {
     rc = gemv_dispatch(m->wdtype, DE_RESIDUAL, a, s);
     if (rc) return rc;
     // ---- FeedForward
-    decode_ln_kernel<<<1, 256, 0, s>>>(m->x, L.ln2_scale, L.shift2, m->y, d, m->shift_tokens);
-    PG_LAUNCH_CHECK();
     a = GemvArgs{};
-    a.wt = L.win_t; a.x = m->y; a.bias = L.bin; a.out = m->u; a.K = d;
+    a.wt = L.win_t; a.x = m->x; a.bias = L.bin; a.out = m->u; a.K = d;
+    a.ln_scale = L.ln2_scale; a.ln_prev = L.shift2; a.ln_shift = m->shift_tokens; a.pos = m->pos;
     const float* last = m->u;
     int last_k = hid;
     if (L.kind == 0) {            // GLU: rows [0,hid) value, [hid,2hid) gate
@@ -321,10 +357,9 @@ int progen_decode_step(const progen_decode_t* m, int do_sample, void* stream) {
     rc = gemv_dispatch(m->wdtype, DE_RESIDUAL, a, s);
     if (rc) return rc;
   }
-  decode_ln_kernel<<<1, 256, 0, s>>>(m->x, m->lnf_scale, nullptr, m->y, d, 0);
-  PG_LAUNCH_CHECK();
   GemvArgs a{};
-  a.wt = m->whead_t; a.x = m->y; a.bias = m->bhead; a.out = m->logits; a.N = m->V; a.K = d;
+  a.wt = m->whead_t; a.x = m->x; a.bias = m->bhead; a.out = m->logits; a.N = m->V; a.K = d;
+  a.ln_scale = m->lnf_scale; a.ln_prev = nullptr; a.ln_shift = 0;                         // final LayerNorm fused (progen.py:220)
   int rc = gemv_dispatch(m->wdtype, DE_BIAS, a, s);
   if (rc) return rc;
   int threads = 32;

@@ -141,6 +141,51 @@ __global__ void ln_shift_bwd_kernel(const TO* __restrict__ dy, long long lddy, c
     const int pos = (int)(t % seq_len);
     const bool has_next = pos + 1 < seq_len;
     float s1 = 0.f, s2 = 0.f;
+    if constexpr (NCH <= 4) {
+      // d <= 512: the row fits in registers — read x, dy and the residual gradient once, all loads issued up front
+      float xh[NCH][4], gs[NCH][4], rr[NCH][4];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c = ch * 128 + lane * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { xh[ch][i] = 0.f; gs[ch][i] = 0.f; rr[ch][i] = 0.f; }
+        if (c < d) {
+          float sc[4];
+          load4<TI>(xr + c, xh[ch]);
+          load4<float>(scale + c, sc);
+          if (!shift || c >= half) load4<TO>(dy + t * lddy + c, gs[ch]);
+          else if (has_next) load4<TO>(dy + (t + 1) * lddy + c, gs[ch]);
+          if constexpr (RESIDUAL) load4<float>(dres + t * (long long)d + c, rr[ch]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            xh[ch][i] = (xh[ch][i] - mean) * rstd;
+            ds_acc[ch][i] += gs[ch][i] * xh[ch][i];
+            gs[ch][i] *= sc[i];
+            s1 += gs[ch][i]; s2 += gs[ch][i] * xh[ch][i];
+          }
+        }
+      }
+      s1 = warp_sum(s1) / d;
+      s2 = warp_sum(s2) / d;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c = ch * 128 + lane * 4;
+        if (c < d) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = rstd * (gs[ch][i] - s1 - xh[ch][i] * s2);
+          if constexpr (RESIDUAL) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { rr[ch][i] += o[i]; cs_acc[ch][i] += rr[ch][i]; }
+            store4(dres + t * (long long)d + c, rr[ch]);
+            if (dout) store4(dout + t * ldo + c, rr[ch]);
+          } else {
+            store4(dout + t * ldo + c, o);
+          }
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       const int c = ch * 128 + lane * 4;

@@ -69,8 +69,8 @@ class Decoder:
                 Lr.gn_hist = self._state(zeros(n, hid // 2))
             Lr.kcache = self._state(zeros(n, I))
             Lr.vcache = self._state(zeros(n, I))
-            Lr.shift1 = self._state(zeros(d // 2))
-            Lr.shift2 = self._state(zeros(d // 2))
+            Lr.shift1 = self._state(zeros(2, d // 2))       # double-buffered by position parity (read [pos&1], write [(pos+1)&1])
+            Lr.shift2 = self._state(zeros(2, d // 2))
         m = self.m = DecodeModel()
         m.n, m.d, m.heads, m.dim_head, m.inner, m.window, m.hid, m.V, m.depth = n, d, cfg['heads'], cfg['dim_head'], I, \
             cfg['window_size'], hid, self.V, len(kinds)

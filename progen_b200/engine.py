@@ -97,9 +97,10 @@ class Engine:
         # tensor-core attention kernel needs bf16, dim_head 64 and 64-aligned windows; other shapes use the CUDA-core kernel
         self.attn_tc = self.mp and cfg['dim_head'] == 64 and cfg['window_size'] % 64 == 0
         import os
-        self.attn_fwd_kind = os.environ.get('PROGEN_ATTN_FWD', 'mma')
-        if self.attn_fwd_kind == 'tcgen05' and cfg['window_size'] % 128 != 0:
-            self.attn_fwd_kind = 'mma'
+        self.attn_fwd_kind = os.environ.get('PROGEN_ATTN_FWD', 'tcgen05')
+        self.attn_bwd_kind = os.environ.get('PROGEN_ATTN_BWD', 'tcgen05')
+        if cfg['window_size'] % 128 != 0:
+            self.attn_fwd_kind = self.attn_bwd_kind = 'mma'
         d, n, w = cfg['dim'], cfg['seq_len'], cfg['window_size']
         self.d, self.n, self.w, self.V = d, n, w, cfg['num_tokens']
         self.h, self.dh = cfg['heads'], cfg['dim_head']
@@ -350,7 +351,8 @@ class Engine:
 
     def attn_bwd(self, qkv, out, dout, lse, dqkv):
         if self.attn_tc:
-            L.check(self.lib.progen_local_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+            fn = self.lib.progen_local_attn_bwd_tc if self.attn_bwd_kind == 'tcgen05' else self.lib.progen_local_attn_bwd
+            L.check(fn(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                                    self.delta.data_ptr(), self.rot_sin.data_ptr(), self.rot_cos.data_ptr(), self.B,
                                                    self.n, self.w, self.h, self.dh, L.stream()), 'local_attn_bwd')
             return     # rotary backward is fused into the kernel's epilogue
