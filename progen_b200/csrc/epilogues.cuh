@@ -138,15 +138,21 @@ struct WarpStagedIO {
   }
 };
 
+// v[i] += bias[col + i]: the same NV floats for every lane (broadcast), fetched with 16-byte loads
+template <int NV> __device__ __forceinline__ void add_bias(const float* __restrict__ bias, int col, float (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i += 4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + i));
+    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+  }
+}
+
 // Every lane of the calling warp must enter (staged IO is warp-cooperative); `valid` says whether this lane's row exists.
 template <int KIND, typename TO, int NV, typename IO>
 __device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long long row, int col, float (&v)[NV], bool valid) {
   constexpr bool FAST = sizeof(TO) == 2;      // bf16 outputs: hardware tanh is below the output rounding
   if constexpr (KIND == EPI_STORE) {
-    if (e.bias) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + col + i);
-    }
+    if (e.bias) add_bias<NV>(e.bias, col, v);
     io.template store<NV>(reinterpret_cast<TO*>(e.out) + row * e.ldo + col, e.ldo, v, valid);
   } else if constexpr (KIND == EPI_ROTARY) {
     const int pos = (int)(row % e.seq_len);
@@ -188,12 +194,12 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long l
     float r[NV];
     if (e.aux) io.template load<NV>(reinterpret_cast<const float*>(e.aux) + row * e.ldaux + col, e.ldaux, r, valid);
     else io.template load<NV>(const_cast<const float*>(p), e.ldo, r, valid);
+    if (e.bias) add_bias<NV>(e.bias, col, v);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) r[i] += v[i] + (e.bias ? __ldg(e.bias + col + i) : 0.f);
+    for (int i = 0; i < NV; ++i) r[i] += v[i];
     io.template store<NV>(p, e.ldo, r, valid);
   } else if constexpr (KIND == EPI_GLU) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + col + i);
+    add_bias<NV>(e.bias, col, v);
     io.template store<NV>(reinterpret_cast<TO*>(e.out2) + row * e.ldo2 + col, e.ldo2, v, valid);
     TO* po = reinterpret_cast<TO*>(e.out) + row * e.ldo + (col >> 1);
     if constexpr (NV >= 16) {
@@ -208,8 +214,7 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long l
       }
     }
   } else if constexpr (KIND == EPI_GELU) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + col + i);
+    add_bias<NV>(e.bias, col, v);
     io.template store<NV>(reinterpret_cast<TO*>(e.out2) + row * e.ldo2 + col, e.ldo2, v, valid);
     float o[NV];
 #pragma unroll

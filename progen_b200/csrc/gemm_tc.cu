@@ -19,18 +19,32 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 384;           // 4 control warps + 8 epilogue warps (2 per TMEM lane quarter)
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
-template <int BN> struct TileCfg {
+// Epilogue shape per kind.  The math-heavy epilogues (GLU / GELU forward and backward: tanh, two outputs, saved
+// pre-activations) are bound by instruction issue and latency of the epilogue warps, not by the tensor pipe: they get 16
+// epilogue warps (4 per TMEM lane quarter) working on 16-column chunks (small register footprint: 640 threads must fit
+// 64K registers).  The light epilogues keep 8 warps and 32-column chunks.
+template <int KIND> struct EpiCfg {
+  // Measured on B200 (config-2 FF proj_in + GLU): 16 warps / 16-column chunks / 3 smem stages = 0.348 ms vs 0.334 ms for
+  // 8 warps / 32 columns / 4 stages — these GEMMs are bound by L2 traffic (operand re-reads + two outputs), not by the
+  // epilogue's issue rate, so every kind uses the 8-warp shape; the 16-warp shape stays selectable here.
+  static constexpr bool HEAVY = false && (KIND == EPI_GLU || KIND == EPI_GLU_BWD || KIND == EPI_GELU || KIND == EPI_GELU_BWD);
+  static constexpr int EW = HEAVY ? 16 : 8;             // epilogue warps
+  static constexpr int CW = HEAVY ? 16 : 32;            // accumulator columns per tcgen05.ld
+  static constexpr int THREADS = 128 + 32 * EW;         // 4 control warps + epilogue warps
+};
+
+template <int BN, int KIND> struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;           // 16 KiB
   static constexpr int B_BYTES = BN * BK * 2;           // 16 / 32 KiB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;   // 6 (BN=128) / 4 (BN=256)
-  static constexpr int TMEM_COLS = 2 * BN;              // 256 / 512
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + NUM_EPI_WARPS * STAGE_WARP_BYTES;
+  static constexpr int FIXED = 1024 /*align slack*/ + BAR_BYTES + EpiCfg<KIND>::EW * STAGE_WARP_BYTES;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;        // 4 (BN=256, 8 warps) / 3 (BN=256, 16 warps) / 6 (BN=128)
+  static constexpr int TMEM_COLS = 2 * BN;              // 256 / 512
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + FIXED;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -94,6 +108,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int CW> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[CW]) {
+  if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 }
 
 // ---------------------------------------------------------------------------------- UMMA descriptors
@@ -162,10 +192,11 @@ __device__ __forceinline__ bool decode_tile(const GemmDev& g, int t, TileInfo& t
 }
 
 template <int BN, bool A_MN, bool B_MN, int KIND, typename TO>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<KIND>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, KIND>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int EW = EpiCfg<KIND>::EW, CW = EpiCfg<KIND>::CW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -192,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), NUM_EPI_WARPS);   // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), EW);              // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -273,7 +304,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp >= 4) {
     // ===================================================================== epilogue (warps 4..7 <-> TMEM lanes 0..127)
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
-    const int chalf = (warp - 4) >> 2;         // which half of the tile columns this warp drains
+    constexpr int GROUPS = EW / 4;              // warps per TMEM lane quarter
+    constexpr int CHUNKS_PER_GROUP = BN / GROUPS / CW;
+    const int cgroup = (warp - 4) >> 2;        // which slice of the tile columns this warp drains
     const int r_in_tile = q * 32 + lane;
     WarpStagedIO io;
     io.buf = smem_raw + (bar_base - smem_u32(smem_raw)) + Cfg::BAR_BYTES + (warp - 4) * STAGE_WARP_BYTES;
@@ -303,16 +336,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
 #pragma unroll 1
-      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
-        const int col = ti.n0 + c * 32;
+      for (int c = cgroup * CHUNKS_PER_GROUP; c < (cgroup + 1) * CHUNKS_PER_GROUP; ++c) {
+        const int col = ti.n0 + c * CW;
         if (col >= g.N) break;                          // warp-uniform
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);                   // .sync.aligned: executed by the whole warp
+        float v[CW];
+        tmem_ld<CW>(taddr + c * CW, v);                 // .sync.aligned: executed by the whole warp
         if (!has_k) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int i = 0; i < CW; ++i) v[i] = 0.f;
         }
-        if constexpr (KIND == EPI_ROTARY) {
+        if constexpr (KIND == EPI_ROTARY && CW == 32) {
           if (rot_cached) {
             float o[32];
             if ((col & 32) == 0) {                      // first / second half of the head: pairs 0..15 / 16..31
@@ -332,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             continue;
           }
         }
-        epi_apply<KIND, TO, 32>(g.epi, io, row, col, v, valid);
+        epi_apply<KIND, TO, CW>(g.epi, io, row, col, v, valid);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -416,7 +449,7 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t row
 
 template <int BN, bool A_MN, bool B_MN, int KIND, typename TO>
 int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& gd, int tiles, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, KIND>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, KIND, TO>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -424,7 +457,7 @@ int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& gd,
     attr_set = true;
   }
   const int grid = tiles < pg_num_sms() ? tiles : pg_num_sms();
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, gd);
+  kern<<<grid, EpiCfg<KIND>::THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, gd);
   PG_LAUNCH_CHECK();
   return PROGEN_OK;
 }
