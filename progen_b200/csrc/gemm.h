@@ -23,4 +23,7 @@ struct GemmArgs {
 };
 
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream);
+// CTA-pair (cta_group::2, 256x256 tiles) variant for the un-batched activation GEMMs; gemm_tc_launch routes to it
+bool gemm_tc2_eligible(const GemmArgs& g);
+int gemm_tc2_launch(const GemmArgs& g, cudaStream_t stream);
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);

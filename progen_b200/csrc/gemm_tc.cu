@@ -478,6 +478,7 @@ int pg_tensor_map_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint6
 
 int gemm_tc_launch(const GemmArgs& a, cudaStream_t stream) {
   PG_CHECK_ARG(a.in_dtype == PG_BF16);
+  if (gemm_tc2_eligible(a)) return gemm_tc2_launch(a, stream);        // CTA-pair kernel: less L2 operand traffic per FLOP
   PG_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0 && a.batch >= 1 && a.split_k >= 1);
   PG_CHECK_ARG(a.N % 32 == 0);
   PG_CHECK_ARG(a.K % BK == 0);                       // TMA would zero-fill a K tail, but batched operands must not bleed
