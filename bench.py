@@ -196,7 +196,7 @@ def time_dominant_gemm(eng, iters=20):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / iters
     flops = 2.0 * T * d * 2 * hid
-    return dict(kernel='gemm_tc_kernel<256,K-major,MN-major,EPI_GLU> (FF proj_in fwd)', shape=[T, 2 * hid, d], ms=ms,
+    return dict(kernel='gemm_tc2_kernel<MN-major B, EPI_GLU, bf16> (CTA-pair tcgen05, FF proj_in fwd)', shape=[T, 2 * hid, d], ms=ms,
                 tflops=flops / ms / 1e9)
 
 

@@ -49,8 +49,14 @@ struct DirectIO {
   }
 };
 
-constexpr int STAGE_ROW_BYTES = 80;                      // 64 B payload + 16 B pad (bank spread)
-constexpr int STAGE_WARP_BYTES = 32 * STAGE_ROW_BYTES;   // 2560 B per epilogue warp
+constexpr int STAGE_WARP_BYTES = 32 * 64;                // 32 rows x (at most) 64 B per epilogue warp, 128 B aligned
+
+// Byte offset of 16-byte piece q of row r in a warp's staging buffer whose rows hold PPR pieces (dense, no padding).
+// The piece index is XOR-swizzled with the 128-byte line the row sits in, so that BOTH access patterns are
+// bank-conflict free: lane = row (8 consecutive rows, one piece) and lane = (row, piece) in row-major order.
+template <int PPR> __device__ __forceinline__ int stage_off(int r, int q) {
+  return r * (PPR * 16) + ((q ^ ((r * PPR / 8) & (PPR - 1))) << 4);
+}
 
 struct WarpStagedIO {
   uint8_t* buf;          // this warp's staging buffer (generic pointer into shared memory)
@@ -87,14 +93,14 @@ struct WarpStagedIO {
     for (int s = 0; s < BYTES / SW; ++s) {
 #pragma unroll
       for (int q = 0; q < PPR; ++q)
-        *reinterpret_cast<uint4*>(buf + lane * STAGE_ROW_BYTES + q * 16) = pack16<T>(&v[s * (SW / (int)sizeof(T)) + q * EPP]);
+        *reinterpret_cast<uint4*>(buf + stage_off<PPR>(lane, q)) = pack16<T>(&v[s * (SW / (int)sizeof(T)) + q * EPP]);
       __syncwarp();
 #pragma unroll
       for (int it = 0; it < PPR; ++it) {
         const int idx = it * 32 + lane;
         const int r = idx / PPR, q = idx % PPR;
         if ((valid_mask >> r) & 1u) {
-          const uint4 t = *reinterpret_cast<const uint4*>(buf + r * STAGE_ROW_BYTES + q * 16);
+          const uint4 t = *reinterpret_cast<const uint4*>(buf + stage_off<PPR>(r, q));
           *reinterpret_cast<uint4*>(base + (long long)r * ld * (int)sizeof(T) + s * SW + q * 16) = t;
         }
       }
@@ -127,12 +133,12 @@ struct WarpStagedIO {
       for (int it = 0; it < PPR; ++it) {
         const int idx = it * 32 + lane;
         const int r = idx / PPR, q = idx % PPR;
-        *reinterpret_cast<uint4*>(buf + r * STAGE_ROW_BYTES + q * 16) = t[s][it];
+        *reinterpret_cast<uint4*>(buf + stage_off<PPR>(r, q)) = t[s][it];
       }
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < PPR; ++q)
-        unpack16<T>(*reinterpret_cast<const uint4*>(buf + lane * STAGE_ROW_BYTES + q * 16), &v[s * (SW / (int)sizeof(T)) + q * EPP]);
+        unpack16<T>(*reinterpret_cast<const uint4*>(buf + stage_off<PPR>(lane, q)), &v[s * (SW / (int)sizeof(T)) + q * EPP]);
       __syncwarp();
     }
   }
