@@ -254,12 +254,17 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = L.load().progen_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get('PROGEN_PROFILE_RANGE') == '1'    # ncu --profile-from-start off: only the timed steps
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.warmup, total):
         eng.tok.copy_(dev_batches[i][:, :-1].reshape(-1)); eng.labels.copy_(dev_batches[i][:, 1:].reshape(-1))
         tr.step_resident(global_batch=B * world)
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     launches = L.load().progen_launch_count() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
     if world > 1:

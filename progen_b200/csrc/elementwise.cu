@@ -4,6 +4,12 @@
 #include "common.cuh"
 #include "../../include/progen_b200.h"
 
+// ln_stream.cu
+int ln_shift_bwd_stream_launch(const void* dy, long long lddy, int act_dtype, const void* x, long long ldx, int x_dtype,
+                               const float* scale, const float* mean, const float* rstd, float* dres, void* dout,
+                               long long ldo, float* dscale, float* dres_colsum, long long T, int d, int seq_len, int shift,
+                               int residual, cudaStream_t stream);
+
 namespace {
 
 constexpr int ROWS_PER_BLOCK = 8;     // 8 warps, one row each
@@ -537,6 +543,10 @@ int progen_ln_shift_bwd(const void* dy, long long lddy, int act_dtype, const voi
   PG_CHECK_ARG(T > 0 && d % 8 == 0 && d <= 4096 && seq_len > 0 && T % seq_len == 0);
   PG_CHECK_ARG(residual ? (dres != nullptr && x_dtype == PG_F32) : (dout != nullptr));
   cudaStream_t s = (cudaStream_t)stream;
+  // bulk-copy streaming kernel (ln_stream.cu) for the shapes it covers; 1 = not eligible -> row-per-warp kernel below
+  const int rc_stream = ln_shift_bwd_stream_launch(dy, lddy, act_dtype, x, ldx, x_dtype, scale, mean, rstd, dres, dout, ldo,
+                                                   dscale, dres_colsum, T, d, seq_len, shift, residual, s);
+  if (rc_stream <= 0) return rc_stream;
   long long b = (T + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   // row-per-warp with two dependent passes is latency-bound: keep several CTAs resident per SM (grid = k * #SMs)
   const int per_sm = d <= 1024 ? 6 : 3;

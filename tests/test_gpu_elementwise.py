@@ -98,6 +98,75 @@ def test_ln_strided_act_input():
     assert (dscale.double() - sd.grad).abs().max().item() < 1e-3 * sd.grad.abs().max().item()
 
 
+@pytest.mark.parametrize('act', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('d,B,n', [(512, 8, 1024), (1024, 5, 768), (128, 16, 64)])
+def test_ln_bwd_stream_path_residual(act, d, B, n):
+    """Shapes the bulk-copy streaming kernel (ln_stream.cu) takes: many chunks per CTA so every stage wraps several
+    times, sequence boundaries inside chunks' look-ahead rows, residual accumulate + low-precision copy + column sums."""
+    L = _L()
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(d + n)
+    T = B * n
+    x = torch.randn(T, d, generator=g, device=dev) * 1.5 - 0.3
+    scale = torch.randn(d, generator=g, device=dev)
+    y = torch.empty(T, d, device=dev, dtype=act)
+    mean = torch.empty(T, device=dev)
+    rstd = torch.empty(T, device=dev)
+    L.check(L.load().progen_ln_shift_fwd(x.data_ptr(), d, L.F32, scale.data_ptr(), y.data_ptr(), d, L.dt(y), mean.data_ptr(),
+                                         rstd.data_ptr(), T, d, n, 1, L.stream()))
+    xd = x.double().requires_grad_(True)
+    sd = scale.double().requires_grad_(True)
+    ref = shift_ref(ln_ref(xd, sd), n)
+    dy = torch.randn(T, d, generator=g, device=dev).to(act)
+    dres0 = torch.randn(T, d, generator=g, device=dev)
+    dres = dres0.clone()
+    dres_lp = torch.full((T, d), float('nan'), device=dev, dtype=act)
+    dscale = torch.zeros(d, device=dev)
+    csum = torch.zeros(d, device=dev)
+    for use_lp in (True, False):
+        dres.copy_(dres0); dscale.zero_(); csum.zero_()
+        L.check(L.load().progen_ln_shift_bwd(dy.data_ptr(), d, L.dt(dy), x.data_ptr(), d, L.F32, scale.data_ptr(), mean.data_ptr(),
+                                             rstd.data_ptr(), dres.data_ptr(), dres_lp.data_ptr() if use_lp else 0, d,
+                                             dscale.data_ptr(), csum.data_ptr(), T, d, n, 1, 1, L.stream()))
+        if xd.grad is None:
+            ref.backward(dy.double())
+        gs = max(1.0, xd.grad.abs().max().item())
+        assert (dres.double() - (dres0.double() + xd.grad)).abs().max().item() < 1e-4 * gs
+        assert (dscale.double() - sd.grad).abs().max().item() < 1e-3 * max(1.0, sd.grad.abs().max().item())
+        assert (dres_lp.double() - dres.double()).abs().max().item() <= (1e-6 if act == torch.float32 else 0.06)
+        cs_ref = dres.double().sum(0)
+        assert (csum.double() - cs_ref).abs().max().item() < 1e-3 * max(1.0, cs_ref.abs().max().item())
+
+
+def test_ln_bwd_stream_path_strided_nonresidual():
+    """SGU LayerNorm backward at a streaming-kernel shape: bf16 input/output taken as column slices of wider buffers."""
+    L = _L()
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(3)
+    T, C = 8 * 1024, 1024
+    a = torch.randn(T, 2 * C, generator=g, device=dev).bfloat16()
+    scale = torch.randn(C, generator=g, device=dev)
+    y = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+    mean = torch.empty(T, device=dev)
+    rstd = torch.empty(T, device=dev)
+    gate = a[:, C:]
+    L.check(L.load().progen_ln_shift_fwd(gate.data_ptr(), 2 * C, L.BF16, scale.data_ptr(), y.data_ptr(), C, L.BF16,
+                                         mean.data_ptr(), rstd.data_ptr(), T, C, 1024, 0, L.stream()))
+    xd = gate.double().requires_grad_(True)
+    sd = scale.double().requires_grad_(True)
+    ref = ln_ref(xd, sd)
+    dy = torch.randn(T, C, generator=g, device=dev).bfloat16()
+    da = torch.zeros(T, 2 * C, device=dev, dtype=torch.bfloat16)
+    dscale = torch.zeros(C, device=dev)
+    L.check(L.load().progen_ln_shift_bwd(dy.data_ptr(), C, L.BF16, gate.data_ptr(), 2 * C, L.BF16, scale.data_ptr(),
+                                         mean.data_ptr(), rstd.data_ptr(), 0, da[:, C:].data_ptr(), 2 * C, dscale.data_ptr(), 0,
+                                         T, C, 1024, 0, 0, L.stream()))
+    ref.backward(dy.double())
+    assert (da[:, C:].double() - xd.grad).abs().max().item() < 2e-2 * xd.grad.abs().max().item()
+    assert da[:, :C].abs().max().item() == 0
+    assert (dscale.double() - sd.grad).abs().max().item() < 2e-3 * sd.grad.abs().max().item()
+
+
 def test_embed_fwd_bwd_and_colsum():
     L = _L()
     dev = 'cuda'
