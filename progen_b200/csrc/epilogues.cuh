@@ -72,7 +72,8 @@ struct WarpStagedIO {
     }
     return t;
   }
-  template <typename T> static __device__ __forceinline__ void unpack16(const uint4& t, float* v) {
+  // by value: a reference to shared memory makes the compiler read the four words with separate 4-byte LDS
+  template <typename T> static __device__ __forceinline__ void unpack16(const uint4 t, float* v) {
     if constexpr (sizeof(T) == 2) {
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
@@ -107,33 +108,48 @@ struct WarpStagedIO {
       __syncwarp();
     }
   }
+  // load = load_issue (coalesced global loads into raw registers; `p` is only used for address arithmetic, `mask` says
+  // which of the warp's 32 rows exist) + load_finish (transpose through the staging buffer).  (Issuing the next chunk's
+  // loads between the two halves was measured and is slower: the bytes in flight stay capped by registers.  The CTA-pair
+  // kernel gemm_tc2.cu stages this operand with TMA instead.)
+  template <int N, typename T>
+  __device__ __forceinline__ void load_issue(const T* p, long long ld, uint4 (&t)[N * (int)sizeof(T) / 16], unsigned mask) const {
+    constexpr int BYTES = N * (int)sizeof(T);
+    constexpr int SW = BYTES < 64 ? BYTES : 64;
+    constexpr int PPR = SW / 16;
+    constexpr int PASSES = BYTES / SW;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(p - (long long)lane * ld);
+#pragma unroll
+    for (int s = 0; s < PASSES; ++s) {
+#pragma unroll
+      for (int it = 0; it < PPR; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = idx / PPR, q = idx % PPR;
+        t[s * PPR + it] = make_uint4(0u, 0u, 0u, 0u);
+        if ((mask >> r) & 1u)
+          t[s * PPR + it] = *reinterpret_cast<const uint4*>(base + (long long)r * ld * (int)sizeof(T) + s * SW + q * 16);
+      }
+    }
+  }
   template <int N, typename T> __device__ __forceinline__ void load(const T* p, long long ld, float (&v)[N], bool) const {
+    uint4 t[N * (int)sizeof(T) / 16];
+    load_issue<N, T>(p, ld, t, valid_mask);
+    load_finish<N, T>(t, v);
+  }
+  template <int N, typename T>
+  __device__ __forceinline__ void load_finish(const uint4 (&t)[N * (int)sizeof(T) / 16], float (&v)[N]) const {
     constexpr int BYTES = N * (int)sizeof(T);
     constexpr int SW = BYTES < 64 ? BYTES : 64;
     constexpr int PPR = SW / 16;
     constexpr int EPP = 16 / (int)sizeof(T);
     constexpr int PASSES = BYTES / SW;
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(p - (long long)lane * ld);
-    // issue every global load of every pass first (memory-level parallelism), then transpose pass by pass
-    uint4 t[PASSES][PPR];
 #pragma unroll
     for (int s = 0; s < PASSES; ++s) {
 #pragma unroll
       for (int it = 0; it < PPR; ++it) {
         const int idx = it * 32 + lane;
         const int r = idx / PPR, q = idx % PPR;
-        t[s][it] = make_uint4(0u, 0u, 0u, 0u);
-        if ((valid_mask >> r) & 1u)
-          t[s][it] = *reinterpret_cast<const uint4*>(base + (long long)r * ld * (int)sizeof(T) + s * SW + q * 16);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < PASSES; ++s) {
-#pragma unroll
-      for (int it = 0; it < PPR; ++it) {
-        const int idx = it * 32 + lane;
-        const int r = idx / PPR, q = idx % PPR;
-        *reinterpret_cast<uint4*>(buf + stage_off<PPR>(r, q)) = t[s][it];
+        *reinterpret_cast<uint4*>(buf + stage_off<PPR>(r, q)) = t[s * PPR + it];
       }
       __syncwarp();
 #pragma unroll
@@ -270,3 +286,6 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, const IO& io, long l
     }
   }
 }
+
+// kinds whose epilogue reads a second [rows x cols] operand from global memory (residual stream / saved pre-activations)
+template <int KIND> constexpr bool epi_has_aux = KIND == EPI_RESIDUAL || KIND == EPI_GLU_BWD || KIND == EPI_GELU_BWD;

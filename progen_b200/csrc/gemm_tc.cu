@@ -401,39 +401,42 @@ EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; uint64_t inner, outer, stride; uint32_t box_inner, box_outer;
+  const void* ptr; uint64_t inner, outer, stride; uint32_t box_inner, box_outer, elem_bytes, swizzle;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && stride == o.stride && box_inner == o.box_inner &&
-           box_outer == o.box_outer;
+           box_outer == o.box_outer && elem_bytes == o.elem_bytes && swizzle == o.swizzle;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.stride); mix(k.box_inner); mix(k.box_outer);
+    mix(k.inner); mix(k.outer); mix(k.stride); mix(k.box_inner); mix(k.box_outer); mix(k.elem_bytes * 256 + k.swizzle);
     return h;
   }
 };
 
-// 2D bf16 tensor map: inner (contiguous) dimension first; 128B swizzle; OOB reads return zeros.
+// 2D tensor map: inner (contiguous) dimension first; elements of 2 (bf16) or 4 (fp32) bytes; swizzle span 32 / 64 /
+// 128 bytes (= box_inner * elem_bytes for the epilogue boxes); OOB reads return zeros, OOB stores are clipped.
 int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_elems, uint32_t box_inner,
-                   uint32_t box_outer, CUtensorMap* out) {
+                   uint32_t box_outer, CUtensorMap* out, uint32_t elem_bytes = 2, uint32_t swizzle = 128) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  MapKey key{ptr, inner, outer, row_stride_elems, box_inner, box_outer};
+  MapKey key{ptr, inner, outer, row_stride_elems, box_inner, box_outer, elem_bytes, swizzle};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return PROGEN_OK; }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { progen_set_error("cuTensorMapEncodeTiled driver entry point not found"); return PROGEN_ERR_DEVICE; }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint64_t strides[1] = {row_stride_elems * elem_bytes};
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(&m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     progen_set_error("cuTensorMapEncodeTiled failed (CUresult %d) ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r,
@@ -474,6 +477,11 @@ int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDe
 int pg_tensor_map_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_elems, uint32_t box_inner,
                           uint32_t box_outer, CUtensorMap* out) {
   return get_tensor_map(ptr, inner, outer, row_stride_elems, box_inner, box_outer, out);
+}
+// epilogue boxes (gemm_tc2.cu): bf16 or fp32 elements, swizzle span = bytes of one box row
+int pg_tensor_map_2d(const void* ptr, uint32_t elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                     uint32_t box_inner, uint32_t box_outer, uint32_t swizzle_bytes, CUtensorMap* out) {
+  return get_tensor_map(ptr, inner, outer, row_stride_elems, box_inner, box_outer, out, elem_bytes, swizzle_bytes);
 }
 
 int gemm_tc_launch(const GemmArgs& a, cudaStream_t stream) {

@@ -1,11 +1,23 @@
 // CTA-pair tcgen05 GEMM (cta_group::2): D[M,N] = A[M,K] * B[N,K]^T for the activation GEMMs (A K-major, un-batched).
 //
-// Why: with 128x256 tiles the K = 512 GEMMs of this model are bound by L2 -> SM operand traffic (every tile pulls
-// 16 KiB of A + 32 KiB of B per k-block; measured ~10-13 TB/s aggregate).  Two CTAs of a cluster (one TPC) share a
-// 256 x 256 output tile: each loads its 128 rows of A and only HALF of the B tile (16 + 16 KiB per k-block, -33 % L2
-// traffic per FLOP); one tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA reads both halves and writes each
-// CTA's 128 accumulator rows into that CTA's TMEM.  Everything else (TMA ring, TMEM double buffering, 8 epilogue warps
-// with warp-staged IO, fused epilogues) matches gemm_tc.cu.
+// Mainloop — why a CTA pair: with 128x256 tiles the K = 512 GEMMs of this model are bound by L2 -> SM operand traffic
+// (every tile pulls 16 KiB of A + 32 KiB of B per k-block; measured ~10-13 TB/s aggregate).  Two CTAs of a cluster (one
+// TPC) share a 256 x 256 output tile: each loads its 128 rows of A and only HALF of the B tile (16 + 16 KiB per k-block,
+// -33 % L2 traffic per FLOP); one tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA reads both halves and
+// writes each CTA's 128 accumulator rows into that CTA's TMEM.
+//
+// Epilogue — all global traffic goes through TMA boxes, none through per-thread LDG/STG:
+//   The fused epilogues move 0.3-1.1 GB per launch (saved pre-activations in, activations / gradients out).  With
+//   per-thread loads the bytes in flight are capped by registers (one 4 KiB chunk per warp): the GLU-backward GEMM ran at
+//   313 us against a 176 us HBM floor, and the transposition through shared memory kept the LSU pipe 59-75 % busy.  Here
+//   each group of 4 epilogue warps (128 threads = the CTA's 128 accumulator rows; two groups split the 256 columns)
+//   owns a ring of shared-memory SLOTS, one [128 rows x <=128 B] box (+ a second box for the two-output kinds):
+//     - the group's elected thread TMA-loads the second operand (residual / pre-activations) of chunk i+NB-1 into a
+//       slot while chunk i is processed: up to 2 x 16 KiB in flight per group, independent of registers;
+//     - a thread reads ITS row from the slot (TMEM lane == row; the TMA swizzle makes lane-per-row 16-byte accesses
+//       bank-conflict free), combines it with 32 accumulator columns from TMEM and writes the result row back in place;
+//     - fence.proxy.async + 128-thread named barrier, then the elected thread TMA-stores the box (rows beyond M are
+//       clipped by the tensor map) and recycles the slot once the store has read it (cp.async.bulk.wait_group.read).
 //
 // Protocol (r = cluster rank, leader = rank 0):
 //   full[s]   (leader's, count 1): leader producer arrives with expect_tx = bytes of BOTH CTAs; both CTAs' TMA loads
@@ -13,6 +25,7 @@
 //   empty[s]  (one per CTA, count 1): tcgen05.commit.cta_group::2 ... multicast::cluster -> both producers
 //   tfull[a]  (one per CTA, count 1): commit multicast -> both CTAs' epilogue warps
 //   tempty[a] (leader's, count 16): 8 local + 8 remote (mapa) epilogue-warp arrivals
+//   sready[g][b] (per CTA, count 1): slot b of epilogue group g holds chunk i's second operand / is free for chunk i
 #include "tc_ptx.cuh"
 #include "gemm.h"
 
@@ -24,15 +37,33 @@ using namespace tc2;
 constexpr int BM = 128;                 // rows per CTA (256 per pair)
 constexpr int BN = 256;                 // columns per pair; each CTA stages BN/2 rows of B
 constexpr int BK = 64;
-constexpr int EW = 8;
+constexpr int EW = 8;                   // epilogue warps: 2 groups x 4 warps
+constexpr int NGROUP = 2;
+constexpr int CPG = BN / NGROUP / 32;   // 32-column chunks per group per tile
 constexpr int THREADS = 128 + 32 * EW;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KiB
 constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STAGES = 6;
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EW * STAGE_WARP_BYTES;
 constexpr int TMEM_COLS = 2 * BN;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// Per-kind shape of the epilogue slots.  ROWB0: bytes per row of the primary box (the in-place operand for the kinds
+// with a second input, else the first output); ROWB1: bytes per row of the second output box (GLU / GELU forward).
+template <int KIND, typename TO> struct Epi2 {
+  static constexpr bool AUX = epi_has_aux<KIND>;
+  static constexpr int ROWB0 = KIND == EPI_RESIDUAL ? 32 * 4 : KIND == EPI_GLU_BWD ? 64 * (int)sizeof(TO) : 32 * (int)sizeof(TO);
+  static constexpr int ROWB1 = KIND == EPI_GLU ? 16 * (int)sizeof(TO) : KIND == EPI_GELU ? 32 * (int)sizeof(TO) : 0;
+  static constexpr int NB = AUX ? 3 : 2;                       // slots per group
+  static constexpr int SLOT_BYTES = BM * (ROWB0 + ROWB1);      // multiples of 4 KiB: every box stays 1024-byte aligned
+  static constexpr int SLOTS_TOTAL = NGROUP * NB * SLOT_BYTES;
+  static constexpr int ROT_BYTES = KIND == EPI_ROTARY ? EW * STAGE_WARP_BYTES : 0;    // staged sin/cos loads
+  static constexpr int FIXED = 1024 + SLOTS_TOTAL + BAR_BYTES + ROT_BYTES;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + FIXED;
+  static_assert(ROWB0 <= 128 && ROWB0 >= 32 && STAGES >= 3, "epilogue slot shape");
+};
 
 struct Gemm2Dev {
   int M, N, K;
@@ -48,17 +79,42 @@ __device__ __forceinline__ bool decode_tile2(const Gemm2Dev& g, int t, int& m0, 
   return true;
 }
 
+// 16-byte piece q of row r inside a [128 x ROWB] box stored with the TMA swizzle of span ROWB (32 / 64 / 128 bytes)
+template <int ROWB> __device__ __forceinline__ uint32_t box_off(int r, int q) { return (uint32_t)stage_off<ROWB / 16>(r, q); }
+
+// read / write N values of row r from / to a swizzled box (TMEM lane == row: one row per thread)
+template <int ROWB, typename T, int N> __device__ __forceinline__ void box_read(const uint8_t* box, int r, float (&v)[N]) {
+  constexpr int EPP = 16 / (int)sizeof(T);
+  static_assert(N * (int)sizeof(T) == ROWB, "row width");
+#pragma unroll
+  for (int q = 0; q < ROWB / 16; ++q)
+    WarpStagedIO::unpack16<T>(*reinterpret_cast<const uint4*>(box + box_off<ROWB>(r, q)), &v[q * EPP]);
+}
+template <int ROWB, typename T, int N> __device__ __forceinline__ void box_write(uint8_t* box, int r, const float (&v)[N]) {
+  constexpr int EPP = 16 / (int)sizeof(T);
+  static_assert(N * (int)sizeof(T) == ROWB, "row width");
+#pragma unroll
+  for (int q = 0; q < ROWB / 16; ++q)
+    *reinterpret_cast<uint4*>(box + box_off<ROWB>(r, q)) = WarpStagedIO::pack16<T>(&v[q * EPP]);
+}
+
 template <bool B_MN, int KIND, typename TO>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Gemm2Dev g) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_out,
+                const __grid_constant__ CUtensorMap tma_out2, const Gemm2Dev g) {
+  using E = Epi2<KIND, TO>;
+  constexpr int STAGES = E::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t slots_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = slots_base + E::SLOTS_TOTAL;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (14 + s); };
+  auto sready_bar = [&](int grp, int b) { return bar_base + 8u * (16 + grp * 3 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 22;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,10 +123,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int kb_total = g.K / BK;
 
-  if (warp == 0 && lane == 0) { prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_b); }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_b); prefetch_tensormap(&tma_out);
+    if constexpr (E::AUX) prefetch_tensormap(&tma_aux);
+    if constexpr (E::ROWB1 > 0) prefetch_tensormap(&tma_out2);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EW); }
+    for (int grp = 0; grp < NGROUP; ++grp)
+      for (int b = 0; b < E::NB; ++b) mbar_init(sready_bar(grp, b), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -135,65 +197,155 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   } else if (warp >= 4) {
     // ===================================================================== epilogue (each CTA drains its own 128 rows)
     const int q = warp & 3;
-    const int cgroup = (warp - 4) >> 2;
-    constexpr int CHUNKS_PER_GROUP = BN / (EW / 4) / 32;
+    const int grp = (warp - 4) >> 2;
     const int r_in_tile = q * 32 + lane;
-    WarpStagedIO io;
-    io.buf = gen + (bar_base - smem_base) + BAR_BYTES + (warp - 4) * STAGE_WARP_BYTES;
-    io.lane = lane;
+    const bool elected = q == 0 && lane == 0;
+    const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles = g.N / BN;
+    const int total_tiles = m_tiles * n_tiles;
+    const int my_tiles = total_tiles > pair ? (total_tiles - pair + npairs - 1) / npairs : 0;
+    const int nchunks = my_tiles * CPG;
+    // chunk i of this group -> (row of the CTA's 128-row block, first accumulator column)
+    auto chunk_coords = [&](int i, int& row0, int& col) {
+      int m0, n0;
+      decode_tile2(g, pair + (i / CPG) * npairs, m0, n0);
+      row0 = m0 + (int)rank * BM;
+      col = n0 + (grp * CPG + (i % CPG)) * 32;
+    };
+    auto slot_addr = [&](int b) { return slots_base + (uint32_t)((grp * E::NB + b) * E::SLOT_BYTES); };
+    // elected thread: make slot (i % NB) ready for chunk i — TMA-load the second operand, or just mark the slot free
+    auto prepare = [&](int i) {
+      const int b = i % E::NB;
+      if constexpr (E::AUX) {
+        int row0, col;
+        chunk_coords(i, row0, col);
+        mbar_expect_tx(sready_bar(grp, b), BM * E::ROWB0);
+        tma_load_2d(slot_addr(b), &tma_aux, sready_bar(grp, b), KIND == EPI_GLU_BWD ? 2 * col : col, row0);
+      } else {
+        mbar_arrive(sready_bar(grp, b));
+      }
+    };
+    if (elected)
+      for (int i = 0; i < E::NB - 1 && i < nchunks; ++i) prepare(i);
+
+    WarpStagedIO rio;                                   // ROTARY only: staged loads of the sin / cos rows
+    rio.buf = gen + (bar_base - smem_base) + BAR_BYTES + (warp - 4) * STAGE_WARP_BYTES;
+    rio.lane = lane;
+    rio.valid_mask = 0xffffffffu;
+    float rs[KIND == EPI_ROTARY ? 32 : 1], rc[KIND == EPI_ROTARY ? 32 : 1];
+
     int acc = 0;
     uint32_t acc_phase = 0;
-    int m0, n0;
-    for (int t = pair; decode_tile2(g, t, m0, n0); t += npairs) {
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      const int m = m0 + (int)rank * BM + r_in_tile;
-      const long long row = m;
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      const bool valid = m < g.M;
-      io.valid_mask = __ballot_sync(0xffffffffu, valid);
-      float rs[KIND == EPI_ROTARY ? 32 : 1], rc[KIND == EPI_ROTARY ? 32 : 1];
-      bool rot_cached = false;
-      if constexpr (KIND == EPI_ROTARY) {
-        if (g.epi.dim_head == 64) {
-          const long long pos = row % g.epi.seq_len;
-          io.template load<32>(g.epi.rot_sin + pos * 32, 32, rs, true);
-          io.template load<32>(g.epi.rot_cos + pos * 32, 32, rc, true);
-          rot_cached = true;
-        }
-      }
+    uint32_t taddr = 0;
+    long long row = 0;
 #pragma unroll 1
-      for (int c = cgroup * CHUNKS_PER_GROUP; c < (cgroup + 1) * CHUNKS_PER_GROUP; ++c) {
-        const int col = n0 + c * 32;
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);
-        if constexpr (KIND == EPI_ROTARY) {
-          if (rot_cached) {
-            float o[32];
-            if ((col & 32) == 0) {
+    for (int i = 0; i < nchunks; ++i) {
+      int row0, col;
+      chunk_coords(i, row0, col);
+      const int ci = i % CPG;
+      if (ci == 0) {
+        row = row0 + r_in_tile;
+        if constexpr (KIND == EPI_ROTARY) {             // this row's 32 (sin, cos) pairs: dim_head == 64 (launcher)
+          const long long pos = row % g.epi.seq_len;
+          rio.template load<32>(g.epi.rot_sin + pos * 32, 32, rs, true);
+          rio.template load<32>(g.epi.rot_cos + pos * 32, 32, rc, true);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + grp * (CPG * 32);
+      }
+      const int b = i % E::NB;
+      float v[32];
+      tmem_ld32(taddr + ci * 32, v);
+      if (ci == CPG - 1) {                              // accumulator stage fully read by this warp
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(acc), 0));     // the leader's barrier (local or remote)
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      mbar_wait(sready_bar(grp, b), (uint32_t)(i / E::NB) & 1u);
+      uint8_t* box0 = gen + (slot_addr(b) - smem_base);
+      uint8_t* box1 = box0 + BM * E::ROWB0;
+      constexpr bool FAST = sizeof(TO) == 2;
+      if constexpr (KIND == EPI_STORE) {
+        if (g.epi.bias) add_bias<32>(g.epi.bias, col, v);
+        box_write<E::ROWB0, TO, 32>(box0, r_in_tile, v);
+      } else if constexpr (KIND == EPI_ROTARY) {
+        float o[32];
+        if ((col & 32) == 0) {                          // which half of the 64-wide head this chunk covers (static indices)
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                o[i] = v[i] * rc[i >> 1] - v[i + 1] * rs[i >> 1];
-                o[i + 1] = v[i + 1] * rc[i >> 1] + v[i] * rs[i >> 1];
-              }
-            } else {
+          for (int j = 0; j < 32; j += 2) {
+            o[j] = v[j] * rc[j >> 1] - v[j + 1] * rs[j >> 1];
+            o[j + 1] = v[j + 1] * rc[j >> 1] + v[j] * rs[j >> 1];
+          }
+        } else {
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                o[i] = v[i] * rc[16 + (i >> 1)] - v[i + 1] * rs[16 + (i >> 1)];
-                o[i + 1] = v[i + 1] * rc[16 + (i >> 1)] + v[i] * rs[16 + (i >> 1)];
-              }
-            }
-            io.template store<32>(reinterpret_cast<TO*>(g.epi.out) + row * g.epi.ldo + col, g.epi.ldo, o, valid);
-            continue;
+          for (int j = 0; j < 32; j += 2) {
+            o[j] = v[j] * rc[16 + (j >> 1)] - v[j + 1] * rs[16 + (j >> 1)];
+            o[j + 1] = v[j + 1] * rc[16 + (j >> 1)] + v[j] * rs[16 + (j >> 1)];
           }
         }
-        epi_apply<KIND, TO, 32>(g.epi, io, row, col, v, valid);
+        box_write<E::ROWB0, TO, 32>(box0, r_in_tile, o);
+      } else if constexpr (KIND == EPI_RESIDUAL) {
+        float r[32];
+        box_read<E::ROWB0, float, 32>(box0, r_in_tile, r);
+        if (g.epi.bias) add_bias<32>(g.epi.bias, col, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] += v[j];
+        box_write<E::ROWB0, float, 32>(box0, r_in_tile, r);
+      } else if constexpr (KIND == EPI_GLU) {
+        add_bias<32>(g.epi.bias, col, v);
+        box_write<E::ROWB0, TO, 32>(box0, r_in_tile, v);
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_fwd<FAST>(v[2 * j + 1]);
+        box_write<E::ROWB1, TO, 16>(box1, r_in_tile, o);
+      } else if constexpr (KIND == EPI_GELU) {
+        add_bias<32>(g.epi.bias, col, v);
+        box_write<E::ROWB0, TO, 32>(box0, r_in_tile, v);
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = gelu_fwd<FAST>(v[j]);
+        box_write<E::ROWB1, TO, 32>(box1, r_in_tile, o);
+      } else if constexpr (KIND == EPI_GLU_BWD) {
+        float u[64];
+        box_read<E::ROWB0, TO, 64>(box0, r_in_tile, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float dh = v[j], val = u[2 * j], gate = u[2 * j + 1];
+          float gf, gd;
+          gelu_fwd_bwd<FAST>(gate, gf, gd);
+          u[2 * j] = dh * gf;
+          u[2 * j + 1] = dh * val * gd;
+        }
+        box_write<E::ROWB0, TO, 64>(box0, r_in_tile, u);
+      } else if constexpr (KIND == EPI_GELU_BWD) {
+        float u[32];
+        box_read<E::ROWB0, TO, 32>(box0, r_in_tile, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= gelu_bwd<FAST>(u[j]);
+        box_write<E::ROWB0, TO, 32>(box0, r_in_tile, v);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(acc), 0));       // the leader's barrier (local or remote)
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      fence_proxy_async();                              // my shared-memory writes -> visible to the TMA store
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (elected) {
+        if constexpr (KIND == EPI_GLU) {
+          tma_store_2d(&tma_out2, slot_addr(b), col, row0);
+          tma_store_2d(&tma_out, slot_addr(b) + BM * E::ROWB0, col >> 1, row0);
+        } else if constexpr (KIND == EPI_GELU) {
+          tma_store_2d(&tma_out2, slot_addr(b), col, row0);
+          tma_store_2d(&tma_out, slot_addr(b) + BM * E::ROWB0, col, row0);
+        } else {
+          tma_store_2d(&tma_out, slot_addr(b), KIND == EPI_GLU_BWD ? 2 * col : col, row0);
+        }
+        bulk_commit_group();
+        if (i + E::NB - 1 < nchunks) {
+          bulk_wait_group_read<1>();                    // the store of chunk i-1 has read its slot: reuse it
+          prepare(i + E::NB - 1);
+        }
+      }
     }
+    if (elected) bulk_wait_group<0>();                  // every store has completed before shared memory goes away
   }
 
   tcgen05_fence_before();
@@ -202,11 +354,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 }
 
 template <bool B_MN, int KIND, typename TO>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Dev& gd, int tiles, cudaStream_t stream) {
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& taux, const CUtensorMap& tout,
+            const CUtensorMap& tout2, const Gemm2Dev& gd, int tiles, cudaStream_t stream) {
+  using E = Epi2<KIND, TO>;
   auto kern = gemm_tc2_kernel<B_MN, KIND, TO>;
   static bool attr_set = false;
   if (!attr_set) {
-    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E::SMEM_TOTAL));
     attr_set = true;
   }
   int pairs = pg_num_sms() / 2;
@@ -214,14 +368,14 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Dev& gd, in
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cfg.dynamicSmemBytes = E::SMEM_TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, gd));
+  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, taux, tout, tout2, gd));
   PG_LAUNCH_CHECK();
   return PROGEN_OK;
 }
@@ -234,11 +388,18 @@ bool gemm_tc2_eligible(const GemmArgs& a) {
   if (a.in_dtype != PG_BF16 || a.a_mn_major || a.batch != 1 || a.split_k != 1 || a.causal || a.batch_reduce) return false;
   if (a.N % BN != 0 || a.K % BK != 0 || a.M < 2 * BM) return false;
   const bool bm = a.b_mn_major != 0, obf = a.out_dtype == PG_BF16;
+  const int osz = obf ? 2 : 4;
+  // every epilogue pointer / leading dimension must be TMA-addressable (16-byte aligned base and row pitch)
+  auto tma_ok = [](const void* p, long long ld, int esz) { return p && ((uintptr_t)p & 15) == 0 && (ld * esz) % 16 == 0; };
   switch (a.epi_kind) {                               // exactly the combinations instantiated below
-    case EPI_STORE: return true;
-    case EPI_ROTARY: case EPI_GLU: case EPI_GELU: return bm && obf;
-    case EPI_RESIDUAL: return bm;
-    case EPI_GLU_BWD: case EPI_GELU_BWD: return !bm && obf;
+    case EPI_STORE: return tma_ok(a.epi.out, a.epi.ldo, osz);
+    case EPI_ROTARY: return bm && obf && a.epi.dim_head == 64 && a.epi.seq_len % 128 == 0 && tma_ok(a.epi.out, a.epi.ldo, 2);
+    case EPI_GLU: case EPI_GELU:
+      return bm && obf && a.epi.bias && tma_ok(a.epi.out, a.epi.ldo, 2) && tma_ok(a.epi.out2, a.epi.ldo2, 2);
+    case EPI_RESIDUAL:
+      return bm && tma_ok(a.epi.out, a.epi.ldo, 4) && (!a.epi.aux || tma_ok(a.epi.aux, a.epi.ldaux, 4));
+    case EPI_GLU_BWD: case EPI_GELU_BWD:
+      return !bm && obf && tma_ok(a.epi.out, a.epi.ldo, 2) && tma_ok(a.epi.aux, a.epi.ldaux, 2);
     default: return false;
   }
 }
@@ -246,17 +407,48 @@ bool gemm_tc2_eligible(const GemmArgs& a) {
 int gemm_tc2_launch(const GemmArgs& a, cudaStream_t stream) {
   PG_CHECK_ARG(gemm_tc2_eligible(a));
   PG_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0);
-  if (a.epi_kind == EPI_ROTARY) PG_CHECK_ARG(a.epi.seq_len % 32 == 0);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, taux, tout, tout2;
   int rc = pg_tensor_map_2d_bf16(a.A, a.K, a.M, a.lda, BK, BM, &ta);
   if (rc) return rc;
   if (!a.b_mn_major) rc = pg_tensor_map_2d_bf16(a.B, a.K, a.N, a.ldb, BK, BN / 2, &tb);
   else               rc = pg_tensor_map_2d_bf16(a.B, a.N, a.K, a.ldb, 64, BK, &tb);
   if (rc) return rc;
+  const bool bm = a.b_mn_major != 0, obf = a.out_dtype == PG_BF16;
+  const uint32_t osz = obf ? 2 : 4;
+  const EpiArgs& e = a.epi;
+  // epilogue boxes: [128 rows x (cols per chunk)] with the swizzle span of one box row; widths in ELEMENTS of each tensor
+  auto emap = [&](const void* p, uint32_t esz, uint64_t width, long long ld, uint32_t box_cols, CUtensorMap* m) {
+    return pg_tensor_map_2d(p, esz, width, (uint64_t)a.M, (uint64_t)ld, box_cols, BM, box_cols * esz, m);
+  };
+  taux = ta; tout2 = ta;                               // unused maps still have to be valid kernel parameters
+  switch (a.epi_kind) {
+    case EPI_STORE: case EPI_ROTARY: rc = emap(e.out, osz, a.N, e.ldo, 32, &tout); break;
+    case EPI_RESIDUAL:
+      rc = emap(e.out, 4, a.N, e.ldo, 32, &tout);
+      if (!rc) rc = e.aux ? emap(e.aux, 4, a.N, e.ldaux, 32, &taux) : emap(e.out, 4, a.N, e.ldo, 32, &taux);
+      break;
+    case EPI_GLU:
+      rc = emap(e.out2, 2, a.N, e.ldo2, 32, &tout2);
+      if (!rc) rc = emap(e.out, 2, a.N / 2, e.ldo, 16, &tout);
+      break;
+    case EPI_GELU:
+      rc = emap(e.out2, 2, a.N, e.ldo2, 32, &tout2);
+      if (!rc) rc = emap(e.out, 2, a.N, e.ldo, 32, &tout);
+      break;
+    case EPI_GLU_BWD:
+      rc = emap(e.out, 2, 2ull * a.N, e.ldo, 64, &tout);
+      if (!rc) rc = emap(e.aux, 2, 2ull * a.N, e.ldaux, 64, &taux);
+      break;
+    case EPI_GELU_BWD:
+      rc = emap(e.out, 2, a.N, e.ldo, 32, &tout);
+      if (!rc) rc = emap(e.aux, 2, a.N, e.ldaux, 32, &taux);
+      break;
+    default: break;
+  }
+  if (rc) return rc;
   Gemm2Dev gd{a.M, a.N, a.K, a.epi};
   const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
-  const bool bm = a.b_mn_major != 0, obf = a.out_dtype == PG_BF16;
-#define TC2_CASE(BMJ, KIND, TO) return launch2<BMJ, KIND, TO>(ta, tb, gd, tiles, stream)
+#define TC2_CASE(BMJ, KIND, TO) return launch2<BMJ, KIND, TO>(ta, tb, taux, tout, tout2, gd, tiles, stream)
   switch (a.epi_kind) {
     case EPI_STORE:
       if (bm) { if (obf) TC2_CASE(true, EPI_STORE, bf16); else TC2_CASE(true, EPI_STORE, float); }

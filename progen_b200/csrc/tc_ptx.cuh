@@ -98,11 +98,28 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N, bool a_mn
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// TMA store of one box (shared -> global, rows/columns outside the tensor are clipped); bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 }  // namespace tc
 
 // host: cached 2-D bf16 tensor map with 128B swizzle (defined in gemm_tc.cu)
 int pg_tensor_map_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_elems, uint32_t box_inner,
                           uint32_t box_outer, CUtensorMap* out);
+// host: same cache, bf16 (2) or fp32 (4) elements, swizzle span 32 / 64 / 128 bytes
+int pg_tensor_map_2d(const void* ptr, uint32_t elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                     uint32_t box_inner, uint32_t box_outer, uint32_t swizzle_bytes, CUtensorMap* out);
 
 // ------------------------------------------------------------------------------------------------ CTA-pair (cta_group::2)
 namespace tc2 {

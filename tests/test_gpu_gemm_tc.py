@@ -81,3 +81,43 @@ def test_tc_gemm_rotary_dim_head_64_cached_tables():
     assert err <= BF16_OUT_TOL * max(1.0, scale), (err, scale)
     err, scale = run_case(L.BACKEND_TC, torch.bfloat16, 200, 256, 64, False, True, L.EPI_ROTARY, seed=12, seq_len=64, dim_head=64)
     assert err <= BF16_OUT_TOL * max(1.0, scale), (err, scale)
+
+
+# (b_mn, epi) combinations of the CTA-pair kernel (gemm_tc2.cu): TMA-staged epilogue slots
+PAIR_COMBOS = [(True, 0), (False, 0), (True, 1), (True, 2), (True, 3), (True, 4), (False, 5), (False, 6)]
+
+
+@pytest.mark.parametrize('b_mn,epi', PAIR_COMBOS)
+def test_tc2_pair_kernel_many_tiles_row_tail(b_mn, epi):
+    """162 tiles over 74 CTA pairs (every epilogue slot and smem stage wraps several times), a row tail that leaves the
+    second CTA of the last pair partly and the TMA boxes partly outside the matrix, two column tiles."""
+    from progen_b200 import lib as L
+    from gemm_cases import run_case
+    M, N, K = 256 * 80 + 136, 512, 192
+    err, scale = run_case(L.BACKEND_TC, torch.bfloat16, M, N, K, False, b_mn, epi, seed=20 + epi,
+                          seq_len=128 if epi == 1 else None, dim_head=64)
+    assert err <= _tol(epi) * max(1.0, scale), (err, scale)
+
+
+def test_tc2_pair_kernel_fp32_store_and_residual_aux():
+    """fp32 STORE output (128-byte rows in the slot) and the RESIDUAL epilogue reading its input from a second buffer."""
+    from progen_b200 import lib as L
+    from gemm_cases import run_case
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(7)
+    M, N, K = 1024, 256, 128
+    A = torch.randn(M, K, generator=g, device=dev).bfloat16()
+    B = (torch.randn(K, N, generator=g, device=dev) * K ** -0.5).bfloat16()
+    acc = A.double() @ B.double()
+    out = torch.empty(M, N, device=dev)
+    L.gemm(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=N, b_mn=True, out=out, ldo=N, backend=L.BACKEND_TC, in_dtype=L.BF16, out_dtype=L.F32)
+    assert (out.double() - acc).abs().max().item() <= F32_OUT_TOL * acc.abs().max().item()
+    res_in = torch.randn(M, N, generator=g, device=dev)
+    keep = res_in.clone()
+    bias = torch.randn(N, generator=g, device=dev)
+    out2 = torch.empty(M, N, device=dev)
+    L.gemm(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=N, b_mn=True, out=out2, ldo=N, aux=res_in, ldaux=N, bias=bias, epi=L.EPI_RESIDUAL,
+           backend=L.BACKEND_TC, in_dtype=L.BF16, out_dtype=L.F32)
+    ref = keep.double() + acc + bias.double()
+    assert (out2.double() - ref).abs().max().item() <= F32_OUT_TOL * ref.abs().max().item()
+    assert torch.equal(res_in, keep)
