@@ -1,4 +1,6 @@
-// CTA-pair tcgen05 GEMM (cta_group::2): D[M,N] = A[M,K] * B[N,K]^T for the activation GEMMs (A K-major, un-batched).
+// CTA-pair tcgen05 GEMM (cta_group::2): D[M,N] = A[M,K] * B[N,K]^T for the un-batched GEMMs of the model: the activation
+// GEMMs (A K-major, fused epilogues) and the weight gradients dW += X^T dY (both operands MN-major, K = tokens, split
+// over K with a TMA reduce-add epilogue).
 //
 // Mainloop — why a CTA pair: with 128x256 tiles the K = 512 GEMMs of this model are bound by L2 -> SM operand traffic
 // (every tile pulls 16 KiB of A + 32 KiB of B per k-block; measured ~10-13 TB/s aggregate).  Two CTAs of a cluster (one
@@ -52,7 +54,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // with a second input, else the first output); ROWB1: bytes per row of the second output box (GLU / GELU forward).
 template <int KIND, typename TO> struct Epi2 {
   static constexpr bool AUX = epi_has_aux<KIND>;
-  static constexpr int ROWB0 = KIND == EPI_RESIDUAL ? 32 * 4 : KIND == EPI_GLU_BWD ? 64 * (int)sizeof(TO) : 32 * (int)sizeof(TO);
+  static constexpr int ROWB0 = (KIND == EPI_RESIDUAL || KIND == EPI_ACCUM) ? 32 * 4 : KIND == EPI_GLU_BWD ? 64 * (int)sizeof(TO) : 32 * (int)sizeof(TO);
   static constexpr int ROWB1 = KIND == EPI_GLU ? 16 * (int)sizeof(TO) : KIND == EPI_GELU ? 32 * (int)sizeof(TO) : 0;
   static constexpr int NB = AUX ? 3 : 2;                       // slots per group
   static constexpr int SLOT_BYTES = BM * (ROWB0 + ROWB1);      // multiples of 4 KiB: every box stays 1024-byte aligned
@@ -67,15 +69,23 @@ template <int KIND, typename TO> struct Epi2 {
 
 struct Gemm2Dev {
   int M, N, K;
+  int split_k;                          // work item = (output tile, K slice); > 1 only with the reduce-add epilogue
   EpiArgs epi;
 };
 
-__device__ __forceinline__ bool decode_tile2(const Gemm2Dev& g, int t, int& m0, int& n0) {
+// work item t -> output tile origin and k-block range.  Consecutive items are DIFFERENT tiles (the K slices of one
+// tile are `tiles` items apart), so concurrently finishing CTAs reduce into different addresses.
+__device__ __forceinline__ bool decode_tile2(const Gemm2Dev& g, int t, int& m0, int& n0, int& kb0, int& kb1) {
   const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM);
   const int n_tiles = g.N / BN;
-  if (t >= m_tiles * n_tiles) return false;
-  m0 = (t / n_tiles) * (2 * BM);
-  n0 = (t % n_tiles) * BN;
+  const int tiles = m_tiles * n_tiles;
+  if (t >= tiles * g.split_k) return false;
+  const int tile = t % tiles, sp = t / tiles;
+  m0 = (tile / n_tiles) * (2 * BM);
+  n0 = (tile % n_tiles) * BN;
+  const long long kb_total = g.K / BK;
+  kb0 = (int)(kb_total * sp / g.split_k);
+  kb1 = (int)(kb_total * (sp + 1) / g.split_k);
   return true;
 }
 
@@ -98,7 +108,7 @@ template <int ROWB, typename T, int N> __device__ __forceinline__ void box_write
     *reinterpret_cast<uint4*>(box + box_off<ROWB>(r, q)) = WarpStagedIO::pack16<T>(&v[q * EPP]);
 }
 
-template <bool B_MN, int KIND, typename TO>
+template <bool A_MN, bool B_MN, int KIND, typename TO>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_out,
@@ -121,7 +131,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int kb_total = g.K / BK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_b); prefetch_tensormap(&tma_out);
@@ -146,15 +155,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int m0, n0;
-      for (int t = pair; decode_tile2(g, t, m0, n0); t += npairs) {
-        for (int kb = 0; kb < kb_total; ++kb) {
+      int m0, n0, kb0, kb1;
+      for (int t = pair; decode_tile2(g, t, m0, n0, kb0, kb1); t += npairs) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           const uint32_t lead_full = mapa(full_bar(stage), 0);
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
           const int k0 = kb * BK;
-          tma_load_2d_pair(sa, &tma_a, lead_full, k0, m0 + (int)rank * BM);                     // my 128 rows of A
+          if constexpr (!A_MN) {
+            tma_load_2d_pair(sa, &tma_a, lead_full, k0, m0 + (int)rank * BM);                   // my 128 rows of A
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)                                                   // my 2 x 64 columns of A^T
+              tma_load_2d_pair(sa + i * 8192, &tma_a, lead_full, m0 + (int)rank * BM + 64 * i, k0);
+          }
           if constexpr (!B_MN) {
             tma_load_2d_pair(sb, &tma_b, lead_full, k0, n0 + (int)rank * (BN / 2));             // my 128 rows of B
           } else {
@@ -169,24 +184,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN, false, B_MN);
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN, A_MN, B_MN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      int m0, n0;
-      for (int t = pair; decode_tile2(g, t, m0, n0); t += npairs) {
+      int m0, n0, kb0, kb1;
+      for (int t = pair; decode_tile2(g, t, m0, n0, kb0, kb1); t += npairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);              // both CTAs' epilogues drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kb_total; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);                    // both CTAs' operand tiles have landed
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc<false>(sa);
+          const uint64_t adesc = make_smem_desc<A_MN>(sa);
           const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(k * (B_MN ? (2048 >> 4) : 2)), idesc,
-                           (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * (A_MN ? (2048 >> 4) : 2)),
+                           bdesc + (uint64_t)(k * (B_MN ? (2048 >> 4) : 2)), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           tcgen05_commit_pair(empty_bar(stage));                // frees the stage in BOTH CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -201,13 +216,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int r_in_tile = q * 32 + lane;
     const bool elected = q == 0 && lane == 0;
     const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles = g.N / BN;
-    const int total_tiles = m_tiles * n_tiles;
+    const int total_tiles = m_tiles * n_tiles * g.split_k;
     const int my_tiles = total_tiles > pair ? (total_tiles - pair + npairs - 1) / npairs : 0;
     const int nchunks = my_tiles * CPG;
     // chunk i of this group -> (row of the CTA's 128-row block, first accumulator column)
     auto chunk_coords = [&](int i, int& row0, int& col) {
-      int m0, n0;
-      decode_tile2(g, pair + (i / CPG) * npairs, m0, n0);
+      int m0, n0, kb0, kb1;
+      decode_tile2(g, pair + (i / CPG) * npairs, m0, n0, kb0, kb1);
       row0 = m0 + (int)rank * BM;
       col = n0 + (grp * CPG + (i % CPG)) * 32;
     };
@@ -318,6 +333,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           u[2 * j + 1] = dh * val * gd;
         }
         box_write<E::ROWB0, TO, 64>(box0, r_in_tile, u);
+      } else if constexpr (KIND == EPI_ACCUM) {
+        box_write<E::ROWB0, float, 32>(box0, r_in_tile, v);
       } else if constexpr (KIND == EPI_GELU_BWD) {
         float u[32];
         box_read<E::ROWB0, TO, 32>(box0, r_in_tile, u);
@@ -335,6 +352,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         } else if constexpr (KIND == EPI_GELU) {
           tma_store_2d(&tma_out2, slot_addr(b), col, row0);
           tma_store_2d(&tma_out, slot_addr(b) + BM * E::ROWB0, col, row0);
+        } else if constexpr (KIND == EPI_ACCUM) {
+          tma_reduce_add_2d(&tma_out, slot_addr(b), col, row0);      // out += acc (fp32 add performed by the L2)
         } else {
           tma_store_2d(&tma_out, slot_addr(b), KIND == EPI_GLU_BWD ? 2 * col : col, row0);
         }
@@ -353,11 +372,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 2) { tcgen05_fence_after(); tmem_dealloc_pair<TMEM_COLS>(tmem_base); }
 }
 
-template <bool B_MN, int KIND, typename TO>
+template <bool A_MN, bool B_MN, int KIND, typename TO>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& taux, const CUtensorMap& tout,
             const CUtensorMap& tout2, const Gemm2Dev& gd, int tiles, cudaStream_t stream) {
   using E = Epi2<KIND, TO>;
-  auto kern = gemm_tc2_kernel<B_MN, KIND, TO>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, KIND, TO>;
   static bool attr_set = false;
   if (!attr_set) {
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E::SMEM_TOTAL));
@@ -385,9 +404,17 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tau
 bool gemm_tc2_eligible(const GemmArgs& a) {
   static int enabled = [] { const char* e = getenv("PROGEN_GEMM_2CTA"); return e ? atoi(e) : 1; }();
   if (!enabled) return false;
-  if (a.in_dtype != PG_BF16 || a.a_mn_major || a.batch != 1 || a.split_k != 1 || a.causal || a.batch_reduce) return false;
+  if (a.in_dtype != PG_BF16 || a.batch != 1 || a.causal || a.batch_reduce) return false;
   if (a.N % BN != 0 || a.K % BK != 0 || a.M < 2 * BM) return false;
-  const bool bm = a.b_mn_major != 0, obf = a.out_dtype == PG_BF16;
+  const bool am = a.a_mn_major != 0, bm = a.b_mn_major != 0, obf = a.out_dtype == PG_BF16;
+  if (a.epi_kind == EPI_ACCUM) {
+    // weight gradients dW[M,N] += X^T dY: both operands MN-major, K = tokens.  The K split is re-chosen for 74 CTA pairs
+    // (the caller's split_k targets 148 single CTAs); several slices of one tile need the reduce-add to be allowed.
+    if (!am || !bm || a.epi.tril || a.M % 8 != 0) return false;
+    if (a.split_k > 1 && !a.epi.atomic) return false;
+    return a.epi.out && ((uintptr_t)a.epi.out & 15) == 0 && (a.epi.ldo * 4) % 16 == 0;
+  }
+  if (am || a.split_k != 1) return false;
   const int osz = obf ? 2 : 4;
   // every epilogue pointer / leading dimension must be TMA-addressable (16-byte aligned base and row pitch)
   auto tma_ok = [](const void* p, long long ld, int esz) { return p && ((uintptr_t)p & 15) == 0 && (ld * esz) % 16 == 0; };
@@ -408,7 +435,9 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t stream) {
   PG_CHECK_ARG(gemm_tc2_eligible(a));
   PG_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0);
   CUtensorMap ta, tb, taux, tout, tout2;
-  int rc = pg_tensor_map_2d_bf16(a.A, a.K, a.M, a.lda, BK, BM, &ta);
+  int rc;
+  if (!a.a_mn_major) rc = pg_tensor_map_2d_bf16(a.A, a.K, a.M, a.lda, BK, BM, &ta);
+  else               rc = pg_tensor_map_2d_bf16(a.A, a.M, a.K, a.lda, 64, BK, &ta);
   if (rc) return rc;
   if (!a.b_mn_major) rc = pg_tensor_map_2d_bf16(a.B, a.K, a.N, a.ldb, BK, BN / 2, &tb);
   else               rc = pg_tensor_map_2d_bf16(a.B, a.N, a.K, a.ldb, 64, BK, &tb);
@@ -423,6 +452,7 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t stream) {
   taux = ta; tout2 = ta;                               // unused maps still have to be valid kernel parameters
   switch (a.epi_kind) {
     case EPI_STORE: case EPI_ROTARY: rc = emap(e.out, osz, a.N, e.ldo, 32, &tout); break;
+    case EPI_ACCUM: rc = emap(e.out, 4, a.N, e.ldo, 32, &tout); break;
     case EPI_RESIDUAL:
       rc = emap(e.out, 4, a.N, e.ldo, 32, &tout);
       if (!rc) rc = e.aux ? emap(e.aux, 4, a.N, e.ldaux, 32, &taux) : emap(e.out, 4, a.N, e.ldo, 32, &taux);
@@ -446,10 +476,23 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t stream) {
     default: break;
   }
   if (rc) return rc;
-  Gemm2Dev gd{a.M, a.N, a.K, a.epi};
-  const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
-#define TC2_CASE(BMJ, KIND, TO) return launch2<BMJ, KIND, TO>(ta, tb, taux, tout, tout2, gd, tiles, stream)
+  int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
+  int split = 1;
+  if (a.epi_kind == EPI_ACCUM && a.epi.atomic) {
+    // K slices per tile: fill the 74 CTA pairs as evenly as possible, keep >= 16 k-blocks per slice, prefer fewer slices
+    const int pairs = pg_num_sms() / 2, kb_total = a.K / BK;
+    double best = 0.0;
+    for (int s = 1; s <= 32 && kb_total / s >= 16; ++s) {
+      const int items = tiles * s, waves = (items + pairs - 1) / pairs;
+      const double eff = (double)items / (waves * pairs);
+      if (eff > best + 0.02) { best = eff; split = s; }
+    }
+  }
+  Gemm2Dev gd{a.M, a.N, a.K, split, a.epi};
+  tiles *= split;
+#define TC2_CASE(BMJ, KIND, TO) return launch2<false, BMJ, KIND, TO>(ta, tb, taux, tout, tout2, gd, tiles, stream)
   switch (a.epi_kind) {
+    case EPI_ACCUM: return launch2<true, true, EPI_ACCUM, float>(ta, tb, taux, tout, tout2, gd, tiles, stream);
     case EPI_STORE:
       if (bm) { if (obf) TC2_CASE(true, EPI_STORE, bf16); else TC2_CASE(true, EPI_STORE, float); }
       else { if (obf) TC2_CASE(false, EPI_STORE, bf16); else TC2_CASE(false, EPI_STORE, float); }
