@@ -480,6 +480,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_tc_kernel(const __grid_co
   if (warp == 2) { tcgen05_fence_after(); tmem_dealloc<TMEM_COLS>(tmem_base); }
 }
 
+#include "attn_tc_bwd_pair.cuh"
+
 }  // namespace
 
 extern "C" {
@@ -507,9 +509,26 @@ int progen_local_attn_bwd_tc(const void* qkv, const void* out, const void* dout,
     once = true;
   }
   BwdDev a{B, seq_len, window, heads, (const bf16*)out, (const bf16*)dout, lse, delta, (bf16*)dqkv, rot_sin, rot_cos};
+  cudaStream_t s = (cudaStream_t)stream;
+  static int pair_enabled = [] { const char* e = getenv("PROGEN_ATTN_PAIR"); return e ? atoi(e) : 1; }();
+  if (pair_enabled && window % (2 * RB) == 0) {
+    // two 128-row work items per CTA, one element-wise warp group each (attn_tc_bwd_pair.cuh)
+    static bool once_pair = false;
+    if (!once_pair) {
+      PG_CUDA(cudaFuncSetAttribute(attn_bwd_dq_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dqp::SMEM_BYTES));
+      PG_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dkvp::SMEM_BYTES));
+      once_pair = true;
+    }
+    const long long pitems = (long long)B * heads * (seq_len / (2 * RB));
+    const int pgrid = (int)(pitems < pg_num_sms() ? pitems : pg_num_sms());
+    attn_bwd_dq_pair_kernel<<<pgrid, 384, dqp::SMEM_BYTES, s>>>(tq_row, tq_col, tdo_row, a);
+    PG_LAUNCH_CHECK();
+    attn_bwd_dkv_pair_kernel<<<pgrid, 384, dkvp::SMEM_BYTES, s>>>(tq_row, tq_col, tdo_col, a);
+    PG_LAUNCH_CHECK();
+    return PROGEN_OK;
+  }
   const long long items = (long long)B * heads * (seq_len / RB);
   const int grid = (int)(items < pg_num_sms() ? items : pg_num_sms());
-  cudaStream_t s = (cudaStream_t)stream;
   // dQ: K/V column tiles are 64 rows of the qkv tensor, Q / dO row tiles 128 rows
   attn_bwd_dq_tc_kernel<<<grid, 384, dq::SMEM_BYTES, s>>>(tq_row, tq_col, tdo_row, a);
   PG_LAUNCH_CHECK();

@@ -14,8 +14,9 @@
 //                pipe serves one group while the other group is in its softmax
 //   warp 2     : TMEM allocator
 //   warps 4..7 : softmax group A, warps 8..11: group B — per tile two passes over S straight from TMEM (row max, then
-//                exp2 + bf16 pack into the K-major swizzled P tile the PV MMA reads); (m, l) and the 64 output channels of
-//                the row live in registers:  O = O * exp2(m_old - m_new) + (P V read back from TMEM)
+//                exp2 + bf16 pack into the K-major swizzled P tile the PV MMA reads), 64 columns per tcgen05.ld; (m, l)
+//                and the 64 output channels of the row live in registers:  O = O * exp2(m_old - m_new) + (P V read back
+//                from TMEM one tile late, between the two passes of the next tile, so its MMA latency is never waited for)
 // Tile B has one more K/V tile than A (its causal diagonal tile); A's diagonal tile is a full tile for B.
 // Window 0's zero look-back keys (reference quirk Q1) enter analytically: m starts at 0 and l at w.
 #include "tc_ptx.cuh"
@@ -149,9 +150,11 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + g * BKV, ad + 2 * k, bd + 2 * k, idesc_qk, k > 0);
         tcgen05_commit(s_full(g));
       };
-      auto issue_pv = [&](int g, int st) {
-        mbar_wait(p_full(g), pcount[g] & 1);                               // P_g(j) is in shared memory, S_g is free
+      auto wait_p = [&](int g) {                                           // P_g(j) is in shared memory, S_g is free
+        mbar_wait(p_full(g), pcount[g] & 1);
         ++pcount[g];
+      };
+      auto issue_pv = [&](int g, int st) {
         tcgen05_fence_after();
         const uint32_t pbase = sP + g * P_BYTES;
         const uint64_t vd = make_smem_desc<true>(sKV + st * KV_BYTES + K_BYTES);
@@ -174,22 +177,25 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
           uint32_t nphase = kv_phase;
           if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
           bool next_ready = false;
+          // S_g(j+1) goes FIRST: the group needs it to continue, while P_g(j) V_j is only read back after the next row max
           if (j < nA) {
-            issue_pv(0, stage);
+            wait_p(0);
             if (j + 1 < nA) {
               mbar_wait(kv_full(nstage), nphase);
               next_ready = true;
               issue_qk(0, nstage);
             }
+            issue_pv(0, stage);
           }
-          issue_pv(1, stage);
-          tcgen05_commit(kv_empty(stage));                                 // K_j, V_j free once every MMA so far retires
+          wait_p(1);
           if (j + 1 < nB) {
             if (!next_ready) mbar_wait(kv_full(nstage), nphase);
             issue_qk(1, nstage);
           } else {
             tcgen05_commit(q_empty);                                       // every QK of this pair has been issued
           }
+          issue_pv(1, stage);
+          tcgen05_commit(kv_empty(stage));                                 // K_j, V_j free once every MMA so far retires
           stage = nstage;
           kv_phase = nphase;
         }
@@ -214,52 +220,63 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
       float o[DH];
 #pragma unroll
       for (int i = 0; i < DH; ++i) o[i] = 0.f;
+      float corr_pending = 1.f;
       for (int j = 0; j < nt; ++j, ++tcount) {
         const bool diag = j == nt - 1;
         mbar_wait(s_full(g), tcount & 1);
         tcgen05_fence_after();
-        // pass 1: row maximum (chunks entirely above the diagonal are skipped: warp-uniform)
+        // pass 1: row maximum, 64 columns per TMEM load (halves entirely above the diagonal are skipped: warp-uniform)
         float mx = -INFINITY;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (diag && cc > q) continue;
-          float t[32];
-          tmem_ld32(s_addr + cc * 32, t);
-          if (diag && cc == q) {
+        for (int hc = 0; hc < 2; ++hc) {
+          if (diag && 2 * hc > q) continue;
+          float t[64];
+          tmem_ld64(s_addr + hc * 64, t);
+          if (diag) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i <= lane ? t[i] : -INFINITY);
+            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, hc * 64 + i <= row ? t[i] : -INFINITY);
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, t[i]);
+            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, t[i]);
           }
         }
         const float m_new = fmaxf(m_run, mx * sc);
         const float corr = ex2_approx(m_run - m_new);                       // ex2(-inf) = 0 on the first tile
+        // P_{j-1} V_{j-1} has had the whole row-max pass to complete: fold it in (also frees P_g for pass 2 below)
+        if (j > 0) {
+          mbar_wait(o_full(g), (tcount - 1) & 1);
+          tcgen05_fence_after();
+          float t[64];
+          tmem_ld64(o_addr, t);
+#pragma unroll
+          for (int i = 0; i < DH; ++i) o[i] = o[i] * corr_pending + t[i];
+          tcgen05_fence_before();                                           // O_g read before the next PV overwrites it
+        }
+        corr_pending = corr;
         // pass 2: p = exp2(s c - m), packed to bf16 into the K-major swizzled P tile (sub-tile = 64 keys)
         float rsum = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint8_t* prow = pbase + (cc >> 1) * (BQ * 128);
-          if (diag && cc > q) {
+        for (int hc = 0; hc < 2; ++hc) {
+          uint8_t* prow = pbase + hc * (BQ * 128);
+          if (diag && 2 * hc > q) {
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-              *reinterpret_cast<uint4*>(prow + ((((cc & 1) * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
             continue;
           }
-          float t[32];
-          tmem_ld32(s_addr + cc * 32, t);
+          float t[64];
+          tmem_ld64(s_addr + hc * 64, t);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < 8; ++ch) {
             float p[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float e = ex2_approx(t[ch * 8 + i] * sc - m_new);
-              p[i] = (diag && cc == q && ch * 8 + i > lane) ? 0.f : e;
+              p[i] = (diag && hc * 64 + ch * 8 + i > row) ? 0.f : e;
               rsum += p[i];
             }
             uint4 u;
             u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]); u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-            *reinterpret_cast<uint4*>(prow + ((((cc & 1) * 4 + ch) ^ (row & 7)) << 4)) = u;
+            *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = u;
           }
         }
         l_run = l_run * corr + rsum;
@@ -268,17 +285,15 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
         fence_proxy_async();                                                // generic-proxy smem writes -> async proxy (MMA)
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(g));
-        // consume P_j V_j: this row's 64 output channels
-        mbar_wait(o_full(g), tcount & 1);
+      }
+      {                                                                     // the last tile's P V
+        mbar_wait(o_full(g), (tcount - 1) & 1);
         tcgen05_fence_after();
+        float t[64];
+        tmem_ld64(o_addr, t);
 #pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {
-          float t[32];
-          tmem_ld32(o_addr + hc * 32, t);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[hc * 32 + i] = o[hc * 32 + i] * corr + t[i];
-        }
-        tcgen05_fence_before();                                             // O_g read before the next PV overwrites it
+        for (int i = 0; i < DH; ++i) o[i] = o[i] * corr_pending + t[i];
+        tcgen05_fence_before();
       }
       // O / l -> bf16 (this thread's whole 128-byte row of the head); lse in natural-log units
       const long long t = (long long)it.b * a.n + it.q0 + g * BQ + row;
