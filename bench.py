@@ -200,6 +200,19 @@ def time_dominant_gemm(eng, iters=20):
                 tflops=flops / ms / 1e9)
 
 
+def dominant_kernel_traffic(config, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of scripts/dominant_gemm.py (profiles/r01_dominant_kernel.json); null for any other shape."""
+    p = os.path.join(ROOT, 'profiles', 'r01_dominant_kernel.json')
+    try:
+        j = json.load(open(p))
+        if j.get('config') == config and j.get('batch') == batch:
+            return j['dram_bytes_per_launch']
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -298,12 +311,17 @@ def main():
         train_flops = 3.0 * fwd_flops_per_token(kw)
         achieved = tps * train_flops / 1e12 / world
         dom = time_dominant_gemm(eng) if not args.fp32 else None
-        roofline = dict(bound='tensor', achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s', frac=achieved / peaks['sustained'],
-                        traffic=None, peak_source=peaks['source'] + ', sustained figure (kernel timed inside a long step)',
-                        definition='whole step: tokens/s x 3 x F_fwd (SURVEY 8d, %.2f MFLOP/token train) per GPU' % (train_flops / 1e6))
+        whole_step = dict(achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s', frac=achieved / peaks['sustained'],
+                          peak_source=peaks['source'] + ', sustained figure (kernels timed inside a long step)',
+                          definition='whole step: tokens/s x 3 x F_fwd (SURVEY 8d, %.2f MFLOP/token train) per GPU' % (train_flops / 1e6))
         if dom:
-            roofline['dominant_kernel'] = dict(dom, peak=peaks['burst'], frac=dom['tflops'] / peaks['burst'],
-                                               peak_source=peaks['source'] + ', burst figure (kernel timed alone)')
+            # the dominant kernel, timed alone with CUDA events just above: algorithmic FLOPs of one launch / its duration
+            roofline = dict(bound='tensor', achieved=dom['tflops'], peak=peaks['burst'], unit='TFLOP/s',
+                            frac=dom['tflops'] / peaks['burst'], traffic=dominant_kernel_traffic(args.config, B),
+                            kernel=dom['kernel'], shape=dom['shape'], ms=dom['ms'],
+                            peak_source=peaks['source'] + ', burst figure (kernel timed alone)', whole_step=whole_step)
+        else:
+            roofline = dict(bound='tensor', traffic=None, **whole_step)
         line = dict(metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f32' if args.fp32 else 'bf16', data='synthetic',

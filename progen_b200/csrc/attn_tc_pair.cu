@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
         mbar_wait(s_full(g), tcount & 1);
         tcgen05_fence_after();
         // pass 1: row maximum, 64 columns per TMEM load (halves entirely above the diagonal are skipped: warp-uniform)
-        float mx = -INFINITY;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains: a single one is 128 dependent FMNMX
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
           if (diag && 2 * hc > q) continue;
@@ -234,12 +234,13 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
           tmem_ld64(s_addr + hc * 64, t);
           if (diag) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, hc * 64 + i <= row ? t[i] : -INFINITY);
+            for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], hc * 64 + i <= row ? t[i] : -INFINITY);
           } else {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, t[i]);
+            for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], t[i]);
           }
         }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const float m_new = fmaxf(m_run, mx * sc);
         const float corr = ex2_approx(m_run - m_new);                       // ex2(-inf) = 0 on the first tile
         // P_{j-1} V_{j-1} has had the whole row-max pass to complete: fold it in (also frees P_g for pass 2 below)
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
         }
         corr_pending = corr;
         // pass 2: p = exp2(s c - m), packed to bf16 into the K-major swizzled P tile (sub-tile = 64 keys)
-        float rsum = 0.f;
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
           uint8_t* prow = pbase + hc * (BQ * 128);
@@ -272,14 +273,14 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_pair_kernel(const __grid_cons
             for (int i = 0; i < 8; ++i) {
               const float e = ex2_approx(t[ch * 8 + i] * sc - m_new);
               p[i] = (diag && hc * 64 + ch * 8 + i > row) ? 0.f : e;
-              rsum += p[i];
+              rs4[i & 3] += p[i];
             }
             uint4 u;
             u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]); u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
             *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = u;
           }
         }
-        l_run = l_run * corr + rsum;
+        l_run = l_run * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
         m_run = m_new;
         tcgen05_fence_before();                                             // my reads of S_g precede the next QK into it
         fence_proxy_async();                                                // generic-proxy smem writes -> async proxy (MMA)
