@@ -147,7 +147,7 @@ def cpu_port_tokens_per_sec(kw, steps, warmup, rows=1, seed=123, budget_s=60.0):
     if not times:
         times = [first]
     sec = sum(times) / len(times)
-    return rows * n / sec, sec, rows
+    return rows * n / sec, sec, rows, len(times)
 
 
 def run_reference_arm(args, cfgd):
@@ -156,10 +156,11 @@ def run_reference_arm(args, cfgd):
         return
     kw = cfgd['kwargs']
     cores = cpu_threads()
-    # bounded sample: one sequence per step, at most 3 timed steps + 1 warm-up (~40 s each on the box host cores)
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    tps, sec, rows = cpu_port_tokens_per_sec(kw, steps, warmup, rows=1)
-    sample = f"{rows} sequence x {kw['seq_len']} tokens per step (fwd+bwd, fp32), {steps} timed steps (of --steps {args.steps})"
+    # bounded sample: one sequence per step; the loop stops once ~60 s of timed work has accumulated (a step takes
+    # 0.6 s on an idle box and up to 40 s on a loaded one), so the whole arm ends within a few minutes either way
+    steps, warmup = max(1, min(args.steps, 50)), max(1, min(args.warmup, 2))
+    tps, sec, rows, timed = cpu_port_tokens_per_sec(kw, steps, warmup, rows=1)
+    sample = f"{rows} sequence x {kw['seq_len']} tokens per step (fwd+bwd, fp32), {timed} timed steps (of --steps {args.steps})"
     line = dict(impl='reference', metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', config=dict(workload=cfgd['name']),
@@ -333,9 +334,9 @@ def main():
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline, final_loss=final_loss)
         if not args.no_cpu_baseline and world == 1:
             cores = cpu_threads()
-            v, sec, rows = cpu_port_tokens_per_sec(kw, steps=1, warmup=1, rows=1)
+            v, sec, rows, timed = cpu_port_tokens_per_sec(kw, steps=30, warmup=1, rows=1, budget_s=20.0)
             line['cpu_baseline'] = dict(value=v, unit='tokens/s', cores=cores, kind='port',
-                                        sample=f'{rows} sequences x {n} tokens, fwd+bwd fp32, 1 timed step ({sec:.1f} s)')
+                                        sample=f'{rows} sequence x {n} tokens per step, fwd+bwd fp32, {timed} timed steps of {sec:.2f} s')
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
