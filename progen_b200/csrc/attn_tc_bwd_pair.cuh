@@ -7,8 +7,9 @@
 //   * each item has its own group of 4 element-wise warps with thread == row (TMEM lane == row), so nothing is
 //     exchanged between threads (the single-item kernels split a row between two warps and meet in a 256-thread
 //     barrier every step) and the two groups drift freely: while one group waits for its MMAs the other computes;
-//   * the MMA warp issues a group's NEXT S / dP as soon as that group has read the current one out of TMEM, i.e.
-//     before its dS tile is written, so the score MMAs run under the element-wise work of the same group.
+//   * each group has its OWN MMA-issuing thread, which issues the group's NEXT S / dP as soon as the group has read
+//     the current one out of TMEM, i.e. before its dS tile is written, so the score MMAs run under the element-wise
+//     work of the same group and neither group's ready work ever queues behind the other group's barrier.
 // The single-item kernels stay for window % 256 != 0.
 
 // ===================================================================================================== dQ, paired
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_pair_kernel(const __grid_c
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_qkv); prefetch_tensormap(&tmap_kv); prefetch_tensormap(&tmap_do); }
   if (warp == 1 && lane == 0) {
-    mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    mbar_init(qdo_full, 1); mbar_init(qdo_empty, 2);                            // one release per group's MMA issuer
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(sd_full(g), 1); mbar_init(sd_empty(g), 4); mbar_init(dq_full(g), 1); mbar_init(dq_empty(g), 4);
       for (int b = 0; b < 2; ++b) { mbar_init(ds_full(g, b), 4); mbar_init(ds_empty(g, b), 1); }
@@ -100,22 +101,25 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_pair_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 3) {
+    // one MMA issuer PER GROUP (warp 1 -> A, warp 3 -> B): a single in-order issuer serving both groups blocks one
+    // group's ready work behind the other group's barrier (ncu: 21 % of the samples in the S/dP wait)
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(RB, CT, false, false);      // [128 x 64] = A (K-major) x B^T (K-major), K = dh
       constexpr uint32_t idesc_a = make_idesc(RB, DH, false, true);       // [128 x 64] += dS (K-major, K = keys) x K_j (MN-major)
+      const int g = warp == 1 ? 0 : 1;
       int stage = 0;
       uint32_t kv_phase = 0, q_phase = 0, item = 0;
-      uint32_t s_issued[2] = {0, 0}, ds_used[2] = {0, 0};
+      uint32_t s_issued = 0, ds_used = 0;
       QPair it;
-      auto issue_s = [&](int g, int st) {
-        if (s_issued[g] > 0) mbar_wait(sd_empty(g), (s_issued[g] - 1) & 1);        // group g has read its previous S / dP
-        ++s_issued[g];
+      const uint32_t tm = tmem_base + g * TM_GROUP;
+      auto issue_s = [&](int st) {
+        if (s_issued > 0) mbar_wait(sd_empty(g), (s_issued - 1) & 1);             // the group has read its previous S / dP
+        ++s_issued;
         tcgen05_fence_after();
         const uint64_t qd = make_smem_desc<false>(sQDO + (2 * g) * ROW_TILE_BYTES);
         const uint64_t dod = make_smem_desc<false>(sQDO + (2 * g + 1) * ROW_TILE_BYTES);
         const uint64_t kd = make_smem_desc<false>(sKV + st * KV_BYTES), vd = make_smem_desc<false>(sKV + st * KV_BYTES + COL_TILE_BYTES);
-        const uint32_t tm = tmem_base + g * TM_GROUP;
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tm, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
 #pragma unroll
@@ -125,38 +129,38 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_pair_kernel(const __grid_c
       for (int wi = blockIdx.x; decode_qpair(a, wi, it); wi += gridDim.x, ++item) {
         mbar_wait(qdo_full, q_phase);
         q_phase ^= 1;
-        const int n_of[2] = {it.nA, it.nA + 2};
+        const int n_g = it.nA + 2 * g, n_all = it.nA + 2;
         mbar_wait(kv_full(stage), kv_phase);
-        issue_s(0, stage);
-        issue_s(1, stage);
-        for (int j = 0; j < n_of[1]; ++j) {
+        issue_s(stage);
+        for (int j = 0; j < n_all; ++j) {
           int nstage = stage + 1;
           uint32_t nphase = kv_phase;
           if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
-          if (j + 1 < n_of[1]) {
-            mbar_wait(kv_full(nstage), nphase);
-            if (j + 1 < n_of[0]) issue_s(0, nstage);
-            issue_s(1, nstage);
-          } else {
-            tcgen05_commit(qdo_empty);                                     // Q / dO tiles no longer needed by any pending MMA
-          }
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (j >= n_of[g]) continue;
-            const uint32_t buf = ds_used[g] & 1;
-            mbar_wait(ds_full(g, buf), (ds_used[g] >> 1) & 1);
-            ++ds_used[g];
+          if (j < n_g) {
+            if (j + 1 < n_g) {
+              mbar_wait(kv_full(nstage), nphase);
+              issue_s(nstage);
+            } else {
+              tcgen05_commit(qdo_empty);                                   // this group's Q / dO tiles are no longer needed
+            }
+            const uint32_t buf = ds_used & 1;
+            mbar_wait(ds_full(g, buf), (ds_used >> 1) & 1);
+            ++ds_used;
             if (j == 0 && item > 0) mbar_wait(dq_empty(g), (item - 1) & 1);   // previous item's dQ has been read out
             tcgen05_fence_after();
             const uint64_t dsd = make_smem_desc<false>(sDS + (2 * g + buf) * ES_BYTES);
             const uint64_t kmn = make_smem_desc<true>(sKV + stage * KV_BYTES);
 #pragma unroll
             for (int k = 0; k < CT / 16; ++k)
-              umma_bf16(tmem_base + g * TM_GROUP + 128, dsd + 2 * k, kmn + (uint64_t)(k * (2048 >> 4)), idesc_a, (j > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tm + 128, dsd + 2 * k, kmn + (uint64_t)(k * (2048 >> 4)), idesc_a, (j > 0 || k > 0) ? 1u : 0u);
             tcgen05_commit(ds_empty(g, buf));
-            if (j == n_of[g] - 1) tcgen05_commit(dq_full(g));
+            if (j == n_g - 1) tcgen05_commit(dq_full(g));
+            tcgen05_commit(kv_empty(stage));                               // my MMAs on K_j / V_j (the other issuer adds its own)
+          } else {
+            // a tile only the other group uses: wait until it has landed (so the arrival lands in the right phase)
+            mbar_wait(kv_full(stage), kv_phase);
+            mbar_arrive(kv_empty(stage));
           }
-          tcgen05_commit(kv_empty(stage));
           stage = nstage;
           kv_phase = nphase;
         }
@@ -284,8 +288,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_pair_kernel(const __grid_
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_qkv_row); prefetch_tensormap(&tmap_qkv_col); prefetch_tensormap(&tmap_do_col); }
   if (warp == 1 && lane == 0) {
-    mbar_init(kvi_full, 1); mbar_init(kvi_empty, 1);
-    for (int s = 0; s < Q_STAGES; ++s) { mbar_init(qs_full(s), 2); mbar_init(qs_empty(s), 1); }   // TMA bytes + the stats warp
+    mbar_init(kvi_full, 1); mbar_init(kvi_empty, 2);                            // one release per group's MMA issuer
+    for (int s = 0; s < Q_STAGES; ++s) { mbar_init(qs_full(s), 2); mbar_init(qs_empty(s), 2); }   // full: TMA bytes + the stats warp
     for (int g = 0; g < 2; ++g) {
       mbar_init(st_full(g), 1); mbar_init(st_empty(g), 4); mbar_init(es_full(g), 4); mbar_init(es_empty(g), 1);
       mbar_init(acc_full(g), 1); mbar_init(acc_empty(g), 4);
@@ -346,22 +350,25 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_pair_kernel(const __grid_
         if (++stage == Q_STAGES) { stage = 0; q_phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
+    // one MMA issuer per group (warp 1 -> A, warp 2 -> B once it has allocated TMEM)
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(RB, CT, false, false);      // S^T / dP^T [128 keys x 64 queries], K = dh
       constexpr uint32_t idesc_a = make_idesc(RB, DH, false, true);       // dV / dK [128 keys x 64 dh], K = queries, B MN-major
+      const int g = warp == 1 ? 0 : 1;
+      const int first_t = 2 * g;                                          // B's keys are not visible to the first two query tiles
       int stage = 0;
       uint32_t q_phase = 0, kv_phase = 0, item = 0;
-      uint32_t st_issued[2] = {0, 0}, es_used[2] = {0, 0};
+      uint32_t st_issued = 0, es_used = 0;
       KPair it;
-      auto issue_st = [&](int g, int st) {
-        if (st_issued[g] > 0) mbar_wait(st_empty(g), (st_issued[g] - 1) & 1);      // group g has read its previous S^T / dP^T
-        ++st_issued[g];
+      const uint32_t tm = tmem_base + g * TM_GROUP;
+      auto issue_st = [&](int st) {
+        if (st_issued > 0) mbar_wait(st_empty(g), (st_issued - 1) & 1);           // the group has read its previous S^T / dP^T
+        ++st_issued;
         tcgen05_fence_after();
         const uint64_t kd = make_smem_desc<false>(sKVr + (2 * g) * ROW_TILE_BYTES);
         const uint64_t vd = make_smem_desc<false>(sKVr + (2 * g + 1) * ROW_TILE_BYTES);
         const uint64_t qd = make_smem_desc<false>(sQS + st * QS_BYTES), dod = make_smem_desc<false>(sQS + st * QS_BYTES + COL_TILE_BYTES);
-        const uint32_t tm = tmem_base + g * TM_GROUP;
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tm, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);
 #pragma unroll
@@ -372,32 +379,34 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_pair_kernel(const __grid_
         mbar_wait(kvi_full, kv_phase);
         kv_phase ^= 1;
         const int nT = it.ntiles;
-        mbar_wait(qs_full(stage), q_phase);
-        issue_st(0, stage);
         for (int t = 0; t < nT; ++t) {
           int nstage = stage + 1;
           uint32_t nphase = q_phase;
           if (nstage == Q_STAGES) { nstage = 0; nphase ^= 1; }
-          if (t + 1 < nT) {
-            mbar_wait(qs_full(nstage), nphase);
-            issue_st(0, nstage);
-            if (t + 1 >= 2) issue_st(1, nstage);
+          if (t < first_t) {
+            // a tile only the other group uses: wait until it has landed (so the arrival lands in the right phase)
+            mbar_wait(qs_full(stage), q_phase);
+            mbar_arrive(qs_empty(stage));
           } else {
-            tcgen05_commit(kvi_empty);                                     // K / V row tiles free for the next item
-          }
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (g == 1 && t < 2) continue;
-            const bool first = t == 2 * g;
-            mbar_wait(es_full(g), es_used[g] & 1);
-            ++es_used[g];
+            if (t == first_t) {
+              mbar_wait(qs_full(stage), q_phase);
+              issue_st(stage);
+            }
+            if (t + 1 < nT) {
+              mbar_wait(qs_full(nstage), nphase);
+              issue_st(nstage);
+            } else {
+              tcgen05_commit(kvi_empty);                                   // this group's K / V row tiles are free for the next item
+            }
+            const bool first = t == first_t;
+            mbar_wait(es_full(g), es_used & 1);
+            ++es_used;
             if (first && item > 0) mbar_wait(acc_empty(g), (item - 1) & 1);
             tcgen05_fence_after();
             const uint64_t ptd = make_smem_desc<false>(sES + (2 * g) * ES_BYTES);
             const uint64_t dsd = make_smem_desc<false>(sES + (2 * g + 1) * ES_BYTES);
             const uint64_t qmn = make_smem_desc<true>(sQS + stage * QS_BYTES);
             const uint64_t domn = make_smem_desc<true>(sQS + stage * QS_BYTES + COL_TILE_BYTES);
-            const uint32_t tm = tmem_base + g * TM_GROUP;
 #pragma unroll
             for (int k = 0; k < CT / 16; ++k)                              // dV += P^T dO_j
               umma_bf16(tm + 192, ptd + 2 * k, domn + (uint64_t)(k * (2048 >> 4)), idesc_a, (!first || k > 0) ? 1u : 0u);
@@ -405,13 +414,12 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_pair_kernel(const __grid_
             for (int k = 0; k < CT / 16; ++k)                              // dK += dS^T Q_j
               umma_bf16(tm + 128, dsd + 2 * k, qmn + (uint64_t)(k * (2048 >> 4)), idesc_a, (!first || k > 0) ? 1u : 0u);
             tcgen05_commit(es_empty(g));
+            tcgen05_commit(qs_empty(stage));                               // my MMAs on Q_j / dO_j (the other issuer adds its own)
           }
-          tcgen05_commit(qs_empty(stage));
           stage = nstage;
           q_phase = nphase;
         }
-        tcgen05_commit(acc_full(0));
-        tcgen05_commit(acc_full(1));
+        tcgen05_commit(acc_full(g));
       }
     }
   } else if (warp >= 4) {
