@@ -75,14 +75,17 @@ struct Gemm2Dev {
 
 // work item t -> output tile origin and k-block range.  Consecutive items are DIFFERENT tiles (the K slices of one
 // tile are `tiles` items apart), so concurrently finishing CTAs reduce into different addresses.
+// A work item covers 256 rows x (CL * 256) columns: with CL == 2 the two pairs of a 4-CTA cluster take adjacent column
+// tiles of the SAME rows (the caller adds pair_index * BN to n0), so the A tile is loaded once and multicast.
+template <int CL>
 __device__ __forceinline__ bool decode_tile2(const Gemm2Dev& g, int t, int& m0, int& n0, int& kb0, int& kb1) {
   const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM);
-  const int n_tiles = g.N / BN;
+  const int n_tiles = g.N / (BN * CL);
   const int tiles = m_tiles * n_tiles;
   if (t >= tiles * g.split_k) return false;
   const int tile = t % tiles, sp = t / tiles;
   m0 = (tile / n_tiles) * (2 * BM);
-  n0 = (tile % n_tiles) * BN;
+  n0 = (tile % n_tiles) * (BN * CL);
   const long long kb_total = g.K / BK;
   kb0 = (int)(kb_total * sp / g.split_k);
   kb1 = (int)(kb_total * (sp + 1) / g.split_k);
@@ -108,7 +111,7 @@ template <int ROWB, typename T, int N> __device__ __forceinline__ void box_write
     *reinterpret_cast<uint4*>(box + box_off<ROWB>(r, q)) = WarpStagedIO::pack16<T>(&v[q * EPP]);
 }
 
-template <bool A_MN, bool B_MN, int KIND, typename TO>
+template <bool A_MN, bool B_MN, int KIND, typename TO, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_out,
@@ -128,9 +131,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // cluster = CL pairs; crank = rank in the cluster, rank = rank inside the pair, pidx = which pair (column tile)
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u, pidx = crank >> 1, lead_crank = crank & ~1u;
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair = blockIdx.x / (2 * CL), npairs = gridDim.x / (2 * CL);      // work-item stream: one per CLUSTER
+  const int ncol = (int)pidx * BN;                                            // my pair's column offset inside the item
+  constexpr uint16_t ALL_CTAS = (uint16_t)((1u << (2 * CL)) - 1u);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_b); prefetch_tensormap(&tma_out);
@@ -138,7 +145,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     if constexpr (E::ROWB1 > 0) prefetch_tensormap(&tma_out2);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }   // empty: every pair's commit
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EW); }
     for (int grp = 0; grp < NGROUP; ++grp)
       for (int b = 0; b < E::NB; ++b) mbar_init(sready_bar(grp, b), 1);
@@ -156,19 +163,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int m0, n0, kb0, kb1;
-      for (int t = pair; decode_tile2(g, t, m0, n0, kb0, kb1); t += npairs) {
+      for (int t = pair; decode_tile2<CL>(g, t, m0, n0, kb0, kb1); t += npairs) {
+        n0 += ncol;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-          const uint32_t lead_full = mapa(full_bar(stage), 0);
+          const uint32_t lead_full = mapa(full_bar(stage), lead_crank);
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
           const int k0 = kb * BK;
-          if constexpr (!A_MN) {
-            tma_load_2d_pair(sa, &tma_a, lead_full, k0, m0 + (int)rank * BM);                   // my 128 rows of A
-          } else {
+          if constexpr (CL == 1) {
+            if constexpr (!A_MN) {
+              tma_load_2d_pair(sa, &tma_a, lead_full, k0, m0 + (int)rank * BM);                 // my 128 rows of A
+            } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)                                                   // my 2 x 64 columns of A^T
-              tma_load_2d_pair(sa + i * 8192, &tma_a, lead_full, m0 + (int)rank * BM + 64 * i, k0);
+              for (int i = 0; i < BM / 64; ++i)                                                 // my 2 x 64 columns of A^T
+                tma_load_2d_pair(sa + i * 8192, &tma_a, lead_full, m0 + (int)rank * BM + 64 * i, k0);
+            }
+          } else if (pidx == 0) {
+            // 4-CTA cluster: pair 0 loads the A rows both pairs use and multicasts them to the same-rank CTA of pair 1
+            const uint16_t mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+            if constexpr (!A_MN) {
+              tma_load_2d_pair_mc(sa, &tma_a, full_bar(stage), mask, k0, m0 + (int)rank * BM);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d_pair_mc(sa + i * 8192, &tma_a, full_bar(stage), mask, m0 + (int)rank * BM + 64 * i, k0);
+            }
           }
           if constexpr (!B_MN) {
             tma_load_2d_pair(sb, &tma_b, lead_full, k0, n0 + (int)rank * (BN / 2));             // my 128 rows of B
@@ -188,7 +208,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       int m0, n0, kb0, kb1;
-      for (int t = pair; decode_tile2(g, t, m0, n0, kb0, kb1); t += npairs) {
+      for (int t = pair; decode_tile2<CL>(g, t, m0, n0, kb0, kb1); t += npairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);              // both CTAs' epilogues drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -202,10 +222,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * (A_MN ? (2048 >> 4) : 2)),
                            bdesc + (uint64_t)(k * (B_MN ? (2048 >> 4) : 2)), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          tcgen05_commit_pair(empty_bar(stage));                // frees the stage in BOTH CTAs
+          tcgen05_commit_pair(empty_bar(stage), ALL_CTAS);      // frees the stage in every CTA of the cluster
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit_pair(tfull_bar(acc));                    // accumulators of both CTAs are complete
+        tcgen05_commit_pair(tfull_bar(acc), (uint16_t)(3u << (2 * pidx)));   // accumulators of both CTAs of MY pair are complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -215,16 +235,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int grp = (warp - 4) >> 2;
     const int r_in_tile = q * 32 + lane;
     const bool elected = q == 0 && lane == 0;
-    const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles = g.N / BN;
+    const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles = g.N / (BN * CL);
     const int total_tiles = m_tiles * n_tiles * g.split_k;
     const int my_tiles = total_tiles > pair ? (total_tiles - pair + npairs - 1) / npairs : 0;
     const int nchunks = my_tiles * CPG;
     // chunk i of this group -> (row of the CTA's 128-row block, first accumulator column)
     auto chunk_coords = [&](int i, int& row0, int& col) {
       int m0, n0, kb0, kb1;
-      decode_tile2(g, pair + (i / CPG) * npairs, m0, n0, kb0, kb1);
+      decode_tile2<CL>(g, pair + (i / CPG) * npairs, m0, n0, kb0, kb1);
       row0 = m0 + (int)rank * BM;
-      col = n0 + (grp * CPG + (i % CPG)) * 32;
+      col = n0 + ncol + (grp * CPG + (i % CPG)) * 32;
     };
     auto slot_addr = [&](int b) { return slots_base + (uint32_t)((grp * E::NB + b) * E::SLOT_BYTES); };
     // elected thread: make slot (i % NB) ready for chunk i — TMA-load the second operand, or just mark the slot free
@@ -274,7 +294,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       if (ci == CPG - 1) {                              // accumulator stage fully read by this warp
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(acc), 0));     // the leader's barrier (local or remote)
+        if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(acc), lead_crank));   // my pair leader's barrier (local or remote)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       mbar_wait(sready_bar(grp, b), (uint32_t)(i / E::NB) & 1u);
@@ -372,31 +392,80 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 2) { tcgen05_fence_after(); tmem_dealloc_pair<TMEM_COLS>(tmem_base); }
 }
 
-template <bool A_MN, bool B_MN, int KIND, typename TO>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& taux, const CUtensorMap& tout,
-            const CUtensorMap& tout2, const Gemm2Dev& gd, int tiles, cudaStream_t stream) {
+// how many clusters of 2*CL CTAs (1 CTA per SM, full shared memory) the device keeps resident at once: the persistent
+// grid must not exceed it, or a late cluster would serialise behind the statically partitioned others
+template <bool A_MN, bool B_MN, int KIND, typename TO, int CL>
+int max_clusters() {
   using E = Epi2<KIND, TO>;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN, KIND, TO>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E::SMEM_TOTAL));
-    attr_set = true;
-  }
-  int pairs = pg_num_sms() / 2;
-  if (tiles < pairs) pairs = tiles;
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, KIND, TO, CL>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E::SMEM_TOTAL) != cudaSuccess) return cached = 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
+  cfg.gridDim = dim3(2 * CL * (pg_num_sms() / (2 * CL)));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = E::SMEM_TOTAL;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  const int cap = pg_num_sms() / (2 * CL);
+  if (getenv("PROGEN_DEBUG")) fprintf(stderr, "[progen] gemm_tc2 kind %d: %d resident clusters of %d CTAs (cap %d)\n", KIND, n, 2 * CL, cap);
+  return cached = (n < cap ? n : cap);
+}
+
+template <bool A_MN, bool B_MN, int KIND, typename TO, int CL>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& taux, const CUtensorMap& tout,
+            const CUtensorMap& tout2, const Gemm2Dev& gd, int items, cudaStream_t stream) {
+  using E = Epi2<KIND, TO>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, KIND, TO, CL>;
+  int clusters = max_clusters<A_MN, B_MN, KIND, TO, CL>();
+  if (clusters <= 0) { progen_set_error("gemm_tc2: no resident cluster of %d CTAs", 2 * CL); return PROGEN_ERR_CUDA; }
+  if (items < clusters) clusters = items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * CL * clusters);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = E::SMEM_TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = 2 * CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   PG_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, taux, tout, tout2, gd));
   PG_LAUNCH_CHECK();
   return PROGEN_OK;
+}
+
+// CL = 2 (4-CTA cluster, A multicast to two pairs) for the mainloop-bound kinds when N holds whole 512-column items
+template <bool A_MN, bool B_MN, int KIND, typename TO>
+int launch2_auto(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& taux, const CUtensorMap& tout,
+                 const CUtensorMap& tout2, Gemm2Dev gd, const GemmArgs& a, cudaStream_t stream) {
+  // Measured (profiles/r01_gemm_bench_4cta.txt): correct, but 3-6 % SLOWER than pairs on the config-2 shapes — clusters of
+  // 4 need two free TPCs in one GPC, so fewer SMs are usable than with pairs, which costs more than the multicast saves.
+  static int quad = [] { const char* e = getenv("PROGEN_GEMM_4CTA"); return e ? atoi(e) : 0; }();
+  const int m_tiles = (a.M + 2 * BM - 1) / (2 * BM);
+  const bool use4 = quad && a.N % (2 * BN) == 0 && max_clusters<A_MN, B_MN, KIND, TO, 2>() > 0;
+  const int cl = use4 ? 2 : 1;
+  const int tiles = m_tiles * (a.N / (BN * cl));
+  const int streams = use4 ? max_clusters<A_MN, B_MN, KIND, TO, 2>() : max_clusters<A_MN, B_MN, KIND, TO, 1>();
+  int split = 1;
+  if (a.epi_kind == EPI_ACCUM && a.epi.atomic && streams > 0) {
+    // K slices per tile: fill the resident clusters as evenly as possible, keep >= 16 k-blocks per slice, prefer fewer slices
+    const int kb_total = a.K / BK;
+    double best = 0.0;
+    for (int s = 1; s <= 48 && kb_total / s >= 16; ++s) {
+      const int items = tiles * s, waves = (items + streams - 1) / streams;
+      const double eff = (double)items / (waves * streams);
+      if (eff > best + 0.02) { best = eff; split = s; }
+    }
+  }
+  gd.split_k = split;
+  if (use4) return launch2<A_MN, B_MN, KIND, TO, 2>(ta, tb, taux, tout, tout2, gd, tiles * split, stream);
+  return launch2<A_MN, B_MN, KIND, TO, 1>(ta, tb, taux, tout, tout2, gd, tiles * split, stream);
 }
 
 }  // namespace
@@ -476,23 +545,10 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t stream) {
     default: break;
   }
   if (rc) return rc;
-  int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
-  int split = 1;
-  if (a.epi_kind == EPI_ACCUM && a.epi.atomic) {
-    // K slices per tile: fill the 74 CTA pairs as evenly as possible, keep >= 16 k-blocks per slice, prefer fewer slices
-    const int pairs = pg_num_sms() / 2, kb_total = a.K / BK;
-    double best = 0.0;
-    for (int s = 1; s <= 32 && kb_total / s >= 16; ++s) {
-      const int items = tiles * s, waves = (items + pairs - 1) / pairs;
-      const double eff = (double)items / (waves * pairs);
-      if (eff > best + 0.02) { best = eff; split = s; }
-    }
-  }
-  Gemm2Dev gd{a.M, a.N, a.K, split, a.epi};
-  tiles *= split;
-#define TC2_CASE(BMJ, KIND, TO) return launch2<false, BMJ, KIND, TO>(ta, tb, taux, tout, tout2, gd, tiles, stream)
+  Gemm2Dev gd{a.M, a.N, a.K, 1, a.epi};
+#define TC2_CASE(BMJ, KIND, TO) return launch2_auto<false, BMJ, KIND, TO>(ta, tb, taux, tout, tout2, gd, a, stream)
   switch (a.epi_kind) {
-    case EPI_ACCUM: return launch2<true, true, EPI_ACCUM, float>(ta, tb, taux, tout, tout2, gd, tiles, stream);
+    case EPI_ACCUM: return launch2_auto<true, true, EPI_ACCUM, float>(ta, tb, taux, tout, tout2, gd, a, stream);
     case EPI_STORE:
       if (bm) { if (obf) TC2_CASE(true, EPI_STORE, bf16); else TC2_CASE(true, EPI_STORE, float); }
       else { if (obf) TC2_CASE(false, EPI_STORE, bf16); else TC2_CASE(false, EPI_STORE, float); }

@@ -182,6 +182,16 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
+// Multicast form: the box lands at the same shared-memory offset of every CTA in `cta_mask`, and (cta_group::2) its bytes
+// are accounted on the barrier at `bar_own_addr`'s offset in the LEADER (even) CTA of each destination's pair — the
+// operand is the issuing CTA's own barrier address with the peer bit cleared, as cute's SM100_TMA_2SM_LOAD_MULTICAST does.
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar_own_addr, uint16_t cta_mask,
+                                                    int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(map), "r"(bar_own_addr & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1) : "memory");
+}
 template <int COLS> __device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem_addr) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "n"(COLS) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -190,9 +200,9 @@ template <int COLS> __device__ __forceinline__ void tmem_dealloc_pair(uint32_t t
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 // commit all prior MMAs of the pair to the barrier at this smem offset in BOTH CTAs
-__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // D[tmem, 256 rows over the CTA pair] (+)= A * B, issued by the leader CTA only
 __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
