@@ -1,6 +1,8 @@
 """Device-resident training state for the train.py loop: parameters, gradients, Adam moments and the apply_every
 accumulator live in flat fp32 buffers; one `step(data)` is one iteration of the reference's inner loop
 (train.py:186-190): loss+grads, optim.update, apply_updates."""
+import os
+
 import numpy as np
 import torch
 
@@ -25,6 +27,7 @@ class Trainer:
         self.gnorm_sq = torch.zeros(1, device=self.eng.dev)
         self.rank, self.world = PAR.world() if data_parallel else (0, 1)
         self._works, self._done = [], []
+        self._bucket, self._bucket_layers = None, max(1, int(os.environ.get('PROGEN_DDP_BUCKET_LAYERS', '3')))
         if self.world > 1:
             # overlap: a layer's weight gradients are all-reduced (async, NCCL's stream) as soon as its backward is done
             self.eng.on_layer_grads = self._reduce_layer
@@ -44,10 +47,22 @@ class Trainer:
         return self._update(sync_loss)
 
     def _reduce_layer(self, i):
+        """Layer i's backward is done (layers arrive in descending order).  Consecutive layers are merged into one
+        bucket of `PROGEN_DDP_BUCKET_LAYERS` layers (default 3): every NCCL kernel holds SMs while it waits for the slowest
+        rank, and the statically partitioned persistent kernels running beside it end late by that long, so fewer, larger
+        all-reduces cost less than one per layer."""
         import torch.distributed as dist
         a, b = self.eng.layer_grad_range(i)
-        self._works.append(dist.all_reduce(self.eng.grads[a:b], op=dist.ReduceOp.SUM, async_op=True))
-        self._done.append((a, b))
+        if self._bucket is None:
+            self._bucket = [a, b, 0]
+        assert b == self._bucket[0] or (a, b) == tuple(self._bucket[:2]), 'layer gradient ranges must be adjacent'
+        self._bucket[0] = min(self._bucket[0], a)
+        self._bucket[2] += 1
+        if self._bucket[2] >= self._bucket_layers or i == 0:
+            lo, hi, _ = self._bucket
+            self._works.append(dist.all_reduce(self.eng.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            self._done.append((lo, hi))
+            self._bucket = None
 
     def _finish_allreduce(self):
         """everything the per-layer reductions did not cover: embedding (final only at the very end of backward), head,
