@@ -31,6 +31,10 @@
 #include "tc_ptx.cuh"
 #include "gemm.h"
 
+#ifndef PROGEN_TMEM_PREFETCH
+#define PROGEN_TMEM_PREFETCH 1
+#endif
+
 namespace {
 
 using namespace tc;
@@ -271,6 +275,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t taddr = 0;
+    uint32_t vr[32];                                    // accumulator chunk in flight (raw TMEM words)
     long long row = 0;
 #pragma unroll 1
     for (int i = 0; i < nchunks; ++i) {
@@ -287,10 +292,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + grp * (CPG * 32);
+        tmem_ld32_issue(taddr, vr);
       }
+#if !PROGEN_TMEM_PREFETCH
+      else tmem_ld32_issue(taddr + ci * 32, vr);
+#endif
       const int b = i % E::NB;
+      tmem_ld32_wait(vr);                               // chunk ci (issued at the end of the previous chunk, or just above)
       float v[32];
-      tmem_ld32(taddr + ci * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
       if (ci == CPG - 1) {                              // accumulator stage fully read by this warp
         tcgen05_fence_before();
         __syncwarp();
@@ -362,6 +373,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         for (int j = 0; j < 32; ++j) v[j] *= gelu_bwd<FAST>(u[j]);
         box_write<E::ROWB0, TO, 32>(box0, r_in_tile, v);
       }
+      // the next chunk's accumulators travel TMEM -> registers while this chunk is fenced, synchronised and stored
+#if PROGEN_TMEM_PREFETCH
+      if (ci + 1 < CPG) tmem_ld32_issue(taddr + (ci + 1) * 32, vr);
+#endif
       fence_proxy_async();                              // my shared-memory writes -> visible to the TMA store
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       else asm volatile("bar.sync 2, 128;" ::: "memory");
