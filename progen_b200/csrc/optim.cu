@@ -47,7 +47,24 @@ __global__ void sqnorm_final_kernel(const float* __restrict__ partial, int nbloc
 struct AdamArgs {
   float lr, b1, b2, eps, wd, max_norm, bc1, bc2;
   int emit;
+  const struct AdamDevState* dev;      // non-null: bias corrections and the emit flag come from device memory (CUDA-graph replay)
 };
+
+// Step-dependent scalars of the optimizer kept on the device, so that a captured CUDA graph of the whole training step
+// can be replayed unchanged: adam_tick_kernel advances them once per step (train.py:189-190 semantics: count, emit).
+struct AdamDevState {
+  long long step;      // Adam count after this step (1-based)
+  float bc1, bc2;      // 1 - b1^step, 1 - b2^step
+  int emit;            // step % apply_every == 0
+};
+
+__global__ void adam_tick_kernel(AdamDevState* st, double b1, double b2, int every) {
+  const long long step = st->step + 1;
+  st->step = step;
+  st->bc1 = (float)(1.0 - pow(b1, (double)step));
+  st->bc2 = (float)(1.0 - pow(b2, (double)step));
+  st->emit = (step % every) == 0 ? 1 : 0;
+}
 
 template <bool WRITE_LP>
 __global__ void adamw_kernel(float* __restrict__ p, bf16* __restrict__ p_lp, const float* __restrict__ g,
@@ -55,6 +72,8 @@ __global__ void adamw_kernel(float* __restrict__ p, bf16* __restrict__ p_lp, con
                              long long n_decay, const float* __restrict__ gnorm_sq, const AdamArgs a) {
   const float gn = sqrtf(gnorm_sq[0]);
   const float clip = a.max_norm / fmaxf(gn, a.max_norm);            // optax.clip_by_global_norm
+  const float bc1 = a.dev ? a.dev->bc1 : a.bc1, bc2 = a.dev ? a.dev->bc2 : a.bc2;
+  const bool emit = a.dev ? a.dev->emit != 0 : a.emit != 0;
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
@@ -72,15 +91,15 @@ __global__ void adamw_kernel(float* __restrict__ p, bf16* __restrict__ p_lp, con
       const float gj = gp[j] * clip;
       mp[j] = a.b1 * mp[j] + (1.f - a.b1) * gj;
       vp[j] = a.b2 * vp[j] + (1.f - a.b2) * gj * gj;
-      float u = (mp[j] / a.bc1) / (sqrtf(vp[j] / a.bc2) + a.eps);
+      float u = (mp[j] / bc1) / (sqrtf(vp[j] / bc2) + a.eps);
       if (i * 4 + j < n_decay) u += a.wd * pp[j];
       ap[j] += -a.lr * u;
-      if (a.emit) { pp[j] += ap[j]; ap[j] = 0.f; }
+      if (emit) { pp[j] += ap[j]; ap[j] = 0.f; }
     }
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
     reinterpret_cast<float4*>(acc)[i] = av;
-    if (a.emit) {
+    if (emit) {
       reinterpret_cast<float4*>(p)[i] = pv;
       if constexpr (WRITE_LP) {
         uint2 t;
@@ -121,7 +140,32 @@ int progen_adamw_step(float* p, void* p_lp, const float* g, float* m, float* v, 
   a.bc1 = (float)(1.0 - pow((double)b1, (double)step));
   a.bc2 = (float)(1.0 - pow((double)b2, (double)step));
   a.emit = emit;
+  a.dev = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
+  long long b = (n / 4 + 255) / 256;
+  const long long cap = (long long)pg_num_sms() * 8;
+  const int blocks = (int)(b > cap ? cap : b);
+  if (p_lp) adamw_kernel<true><<<blocks, 256, 0, s>>>(p, (bf16*)p_lp, g, m, v, acc, n, n_decay, gnorm_sq, a);
+  else adamw_kernel<false><<<blocks, 256, 0, s>>>(p, nullptr, g, m, v, acc, n, n_decay, gnorm_sq, a);
+  PG_LAUNCH_CHECK();
+  return PROGEN_OK;
+}
+
+// Same optimizer call with the step-dependent scalars in device memory (`state`: 32 bytes, see AdamDevState; its `step`
+// field holds the number of calls made so far).  Two launches with launch-invariant arguments, so a captured CUDA graph of
+// a training step stays valid: tick (count, bias corrections, emit = count % apply_every == 0), then the update.
+int progen_adamw_step_dev(float* p, void* p_lp, const float* g, float* m, float* v, float* acc, long long n, long long n_decay,
+                          const float* gnorm_sq, float lr, float b1, float b2, float eps, float wd, float max_norm,
+                          int apply_every, void* state, void* stream) {
+  PG_CHECK_ARG(n > 0 && n % 4 == 0 && n_decay >= 0 && n_decay <= n && apply_every >= 1 && state != nullptr);
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(state) & 7) == 0);
+  AdamArgs a;
+  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd; a.max_norm = max_norm;
+  a.bc1 = a.bc2 = 1.f; a.emit = 0;
+  a.dev = reinterpret_cast<const AdamDevState*>(state);
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, s>>>(reinterpret_cast<AdamDevState*>(state), (double)b1, (double)b2, apply_every);
+  PG_LAUNCH_CHECK();
   long long b = (n / 4 + 255) / 256;
   const long long cap = (long long)pg_num_sms() * 8;
   const int blocks = (int)(b > cap ? cap : b);

@@ -365,14 +365,19 @@ class Engine:
         """data: (B, n+1) integer rows -> (device scalar loss, grads accumulated into self.grads).
         Mirrors utils.py:61-76: ids = data[:, :-1], labels = data[:, 1:], mean over rows of the masked CE.
         `global_batch` (DDP): scale by 1/global_batch so that a SUM all-reduce yields the global-mean gradient."""
+        B = self.load_batch(data)
+        self.step_device(global_batch or B, zero_grads)
+        return self.loss
+
+    def load_batch(self, data):
+        """host (or device) rows (B, n+1) -> self.tok / self.labels; returns B"""
         data = torch.as_tensor(np.asarray(data).astype(np.int32) if not isinstance(data, torch.Tensor) else data)
         B = data.shape[0]
         self.ensure_batch(B)
         dd = data.to(device=self.dev, dtype=torch.int32, non_blocking=True)
         self.tok.copy_(dd[:, :-1].reshape(-1))
         self.labels.copy_(dd[:, 1:].reshape(-1))
-        self.step_device(global_batch or B, zero_grads)
-        return self.loss
+        return B
 
     def step_device(self, global_batch, zero_grads=True):
         """forward + loss + backward on tokens/labels already resident in self.tok / self.labels"""

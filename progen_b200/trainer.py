@@ -27,6 +27,7 @@ class Trainer:
         self.gnorm_sq = torch.zeros(1, device=self.eng.dev)
         self.rank, self.world = PAR.world() if data_parallel else (0, 1)
         self._works, self._done = [], []
+        self._graph, self._graph_key, self._adam_state = None, None, None
         self._bucket, self._bucket_layers = None, max(1, int(os.environ.get('PROGEN_DDP_BUCKET_LAYERS', '3')))
         if self.world > 1:
             # overlap: a layer's weight gradients are all-reduced (async, NCCL's stream) as soon as its backward is done
@@ -38,13 +39,63 @@ class Trainer:
     def step(self, data, sync_loss=False):
         """data: this rank's rows, (b, n+1) integers.  Returns the device scalar loss (global mean when sync_loss)."""
         gb = data.shape[0] * self.world if self.world > 1 else data.shape[0]
+        self._drop_graph_unless(data.shape[0])
+        if self._graph is not None and self._graph_key == (data.shape[0], gb):
+            self.eng.load_batch(data)                      # H2D copies stay outside the graph
+            return self._replay()
         self.eng.loss_and_grad(data, global_batch=gb)
         return self._update(sync_loss)
 
     def step_resident(self, global_batch=None, sync_loss=False):
         """same, on tokens/labels already copied into engine.tok / engine.labels (bench: inputs resident in HBM)"""
-        self.eng.step_device(global_batch or self.eng.B * self.world)
+        gb = global_batch or self.eng.B * self.world
+        self._drop_graph_unless(self.eng.B)
+        if self._graph is not None and self._graph_key == (self.eng.B, gb):
+            return self._replay()
+        self.eng.step_device(gb)
         return self._update(sync_loss)
+
+    # ---- CUDA graph of the whole step (single GPU): forward, loss, backward, norm, AdamW, masked copies = ~285 launches
+    def capture_graph(self, batch_rows, global_batch=None):
+        """Capture one training step for batches of `batch_rows` rows into a CUDA graph; later `step` / `step_resident`
+        calls with that shape replay it.  The step-dependent optimizer scalars live on the device
+        (`progen_adamw_step_dev`), so the graph is identical for every step.  Call after at least one eager step of the
+        same shape (kernel attributes, tensor maps and buffers must exist before capture)."""
+        if self.world > 1:
+            raise L.ProgenError('capture_graph: single-GPU only (the NCCL path overlaps its all-reduces eagerly)')
+        eng = self.eng
+        eng.ensure_batch(batch_rows)
+        gb = global_batch or batch_rows
+        st = torch.zeros(4, dtype=torch.int64, device=eng.dev)          # AdamDevState: count | bc1, bc2 | emit, pad
+        st[0] = self.count
+        self._adam_state = st
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.step_device(gb)
+            self._update_captured()
+        self._graph, self._graph_key = g, (batch_rows, gb)
+        return g
+
+    def _update_captured(self):
+        eng, lib, st = self.eng, L.load(), L.stream()
+        L.check(lib.progen_grad_sqnorm(eng.grads.data_ptr(), eng.n_params_padded, self.ws.data_ptr(), self.gnorm_sq.data_ptr(), st),
+                'grad_sqnorm')
+        L.check(lib.progen_adamw_step_dev(eng.params.data_ptr(), eng.params_lp.data_ptr() if eng.mp else 0, eng.grads.data_ptr(),
+                                          self.m.data_ptr(), self.v.data_ptr(), self.acc.data_ptr(), eng.n_params_padded,
+                                          eng.n_decay, self.gnorm_sq.data_ptr(), self.lr, self.b1, self.b2, self.eps, self.wd,
+                                          self.max_norm, self.every, self._adam_state.data_ptr(), st), 'adamw_step_dev')
+        eng.refresh_masked_copies()                        # every step (a no-op recompute between emits): keeps the graph static
+
+    def _drop_graph_unless(self, batch_rows):
+        """a different batch size re-allocates the engine's activation buffers: the captured pointers would dangle"""
+        if self._graph is not None and batch_rows != self._graph_key[0]:
+            self._graph, self._graph_key = None, None
+
+    def _replay(self):
+        self._graph.replay()
+        self.count += 1
+        return self.eng.loss
 
     def _reduce_layer(self, i):
         """Layer i's backward is done (layers arrive in descending order).  Consecutive layers are merged into one
@@ -86,6 +137,8 @@ class Trainer:
             if sync_loss:
                 PAR.allreduce_scalar_(eng.loss)
         self.count += 1
+        if self._adam_state is not None:
+            self._adam_state[0] = self.count               # keep the device-side count in step with eager steps
         emit = int(self.count % self.every == 0)
         L.check(lib.progen_grad_sqnorm(eng.grads.data_ptr(), eng.n_params_padded, self.ws.data_ptr(), self.gnorm_sq.data_ptr(), st),
                 'grad_sqnorm')
@@ -101,6 +154,7 @@ class Trainer:
         """validation loss (train.py:207-211): forward + loss only"""
         eng = self.eng
         d = torch.as_tensor(np.asarray(data).astype(np.int32) if not isinstance(data, torch.Tensor) else data)
+        self._drop_graph_unless(d.shape[0])
         eng.ensure_batch(d.shape[0])
         dd = d.to(device=eng.dev, dtype=torch.int32)
         eng.tok.copy_(dd[:, :-1].reshape(-1))
