@@ -208,6 +208,8 @@ class Engine:
         if B == self.B:
             return
         self.B = B
+        self.alloc_epoch = getattr(self, 'alloc_epoch', 0) + 1      # activation buffers are re-allocated below: captured
+                                                                    # CUDA graphs (Trainer.capture_graph) become invalid
         T = B * self.n
         self.T = T
         d, I, hid = self.d, self.I, self.hid

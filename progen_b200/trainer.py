@@ -12,7 +12,7 @@ from . import parallel as PAR
 
 class Trainer:
     def __init__(self, model, params, learning_rate=2e-4, weight_decay=1e-3, max_grad_norm=0.5, grad_accum_every=4,
-                 b1=0.9, b2=0.999, eps=1e-8, optim_state=None, data_parallel=True):
+                 b1=0.9, b2=0.999, eps=1e-8, optim_state=None, data_parallel=True, cuda_graph=False):
         self.model = model
         self.eng = model.engine
         self.eng.load_params(params)
@@ -27,7 +27,9 @@ class Trainer:
         self.gnorm_sq = torch.zeros(1, device=self.eng.dev)
         self.rank, self.world = PAR.world() if data_parallel else (0, 1)
         self._works, self._done = [], []
-        self._graph, self._graph_key, self._adam_state = None, None, None
+        self._graph, self._graph_key, self._graph_epoch, self._adam_state = None, None, 0, None
+        # cuda_graph=True: after two eager steps of one batch shape the step is captured and replayed from then on
+        self._auto_graph, self._eager_key, self._eager_run = bool(cuda_graph), None, 0
         self._bucket, self._bucket_layers = None, max(1, int(os.environ.get('PROGEN_DDP_BUCKET_LAYERS', '3')))
         if self.world > 1:
             # overlap: a layer's weight gradients are all-reduced (async, NCCL's stream) as soon as its backward is done
@@ -44,7 +46,15 @@ class Trainer:
             self.eng.load_batch(data)                      # H2D copies stay outside the graph
             return self._replay()
         self.eng.loss_and_grad(data, global_batch=gb)
-        return self._update(sync_loss)
+        loss = self._update(sync_loss)
+        if self._auto_graph and self.world == 1:
+            key = (data.shape[0], gb)
+            self._eager_run = self._eager_run + 1 if key == self._eager_key else 1
+            self._eager_key = key
+            if self._eager_run >= 2:
+                self.capture_graph(data.shape[0], gb)      # capture does not execute: eng.loss still holds this step's value
+                self._eager_run = 0
+        return loss
 
     def step_resident(self, global_batch=None, sync_loss=False):
         """same, on tokens/labels already copied into engine.tok / engine.labels (bench: inputs resident in HBM)"""
@@ -74,7 +84,7 @@ class Trainer:
         with torch.cuda.graph(g):
             eng.step_device(gb)
             self._update_captured()
-        self._graph, self._graph_key = g, (batch_rows, gb)
+        self._graph, self._graph_key, self._graph_epoch = g, (batch_rows, gb), getattr(eng, 'alloc_epoch', 0)
         return g
 
     def _update_captured(self):
@@ -89,8 +99,9 @@ class Trainer:
 
     def _drop_graph_unless(self, batch_rows):
         """a different batch size re-allocates the engine's activation buffers: the captured pointers would dangle"""
-        if self._graph is not None and batch_rows != self._graph_key[0]:
-            self._graph, self._graph_key = None, None
+        if self._graph is not None and (batch_rows != self._graph_key[0] or
+                                        getattr(self.eng, 'alloc_epoch', 0) != self._graph_epoch):
+            self._graph, self._graph_key = None, None      # (model.apply / sampling with another batch size re-allocates too)
 
     def _replay(self):
         self._graph.replay()

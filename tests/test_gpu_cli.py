@@ -33,7 +33,7 @@ def test_train_checkpoint_resume_sample(tmp_path):
     common = ['--config_path', str(cfgdir), '--model_name', 'tiny', '--data_path', str(data), '--checkpoint_path',
               str(tmp_path / 'ckpts'), '--wandb_off', '--batch_size', '4', '--grad_accum_every', '2', '--checkpoint_every', '1',
               '--validate_every', '2', '--sample_every', '3', '--prime_length', '8']
-    out = run([os.path.join(ROOT, 'train.py')] + common + ['--num_steps', '3'], cwd=str(tmp_path))
+    out = run([os.path.join(ROOT, 'train.py')] + common + ['--num_steps', '3', '--cuda_graph'], cwd=str(tmp_path))   # captured after 2 eager micro-steps
     assert 'loss:' in out and 'valid_loss:' in out and 'checkpoint to start at sequence index of 8' in out
     losses = [float(l.split()[-1]) for l in out.splitlines() if l.startswith('loss:')]
     assert len(losses) == 3 and all(l == l and l < 7.0 for l in losses)

@@ -45,9 +45,10 @@ from progen_b200.utils import sample, confirm, exists
 @click.option('--synthetic', default=False, is_flag=True, help='uniform-random tokens instead of --data_path')
 @click.option('--text_file', default=None, help='one sequence per line (train); last 5%% of lines validate')
 @click.option('--num_steps', default=None, type=int, help='stop after this many effective batches')
+@click.option('--cuda_graph', default=False, is_flag=True, help='single GPU: capture the training step into a CUDA graph and replay it')
 def main(seed, batch_size, grad_accum_every, learning_rate, weight_decay, data_parallel, max_grad_norm, validate_every,
          sample_every, checkpoint_every, checkpoint_path, checkpoint_keep_n, config_path, model_name, prime_length, seq_len,
-         mixed_precision, data_path, wandb_off, wandb_project_name, new, synthetic, text_file, num_steps):
+         mixed_precision, data_path, wandb_off, wandb_project_name, new, synthetic, text_file, num_steps, cuda_graph):
     if data_parallel and 'RANK' in os.environ:
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
@@ -72,7 +73,8 @@ def main(seed, batch_size, grad_accum_every, learning_rate, weight_decay, data_p
     else:
         params, optim_state, start_seq_index = model.init(seed), None, 0
     trainer = model.trainer(params, learning_rate=learning_rate, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
-                            grad_accum_every=grad_accum_every, optim_state=optim_state, data_parallel=data_parallel)
+                            grad_accum_every=grad_accum_every, optim_state=optim_state, data_parallel=data_parallel,
+                            cuda_graph=cuda_graph and world == 1)
     seq_len = model_kwargs['seq_len']                           # the --seq_len flag is dead in the reference too (train.py:137)
     num_params = model.engine.num_params
 
