@@ -23,7 +23,8 @@ constexpr int CG = 2;                       // consumer groups: group g takes th
                                             // two stages are in the (latency-bound, ~1.3 us/row) math at any time
 constexpr int CW = RB * CG;                 // consumer warps
 constexpr int THREADS = 32 * (CW + 1);      // + 1 producer warp
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
+constexpr int SMEM_BUDGET = 212 * 1024;          // + 8.3 KiB static (barriers, reduction scratch) stays under 227 KiB
 
 struct LnStreamArgs {
   const void* dy; long long lddy;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(THREADS, 1) ln_shift_bwd_stream_kernel(const L
     // ============================================================ producer: bulk loads in, bulk stores out
     const uint32_t xrow = d * (uint32_t)sizeof(TI), yrow = d * (uint32_t)sizeof(TO), rrow = d * 4u;
     const int dy_rows = a.shift ? RB + 1 : RB;
-    const bool x_contig = a.ldx == d, dy_contig = a.lddy == d, out_contig = a.ldo == d;
+    const bool x_contig = a.ldx == d, dy_contig = a.lddy == d;
     uint32_t tx = RB * xrow + 2 * RB * 4u + (RESIDUAL ? RB * rrow : 0u);
     for (long long it = 0; it < n_my + a.stages; ++it) {
       const int stage = (int)(it % a.stages);
@@ -112,10 +113,6 @@ __global__ void __launch_bounds__(THREADS, 1) ln_shift_bwd_stream_kernel(const L
           bool issued = false;
           if (lane == RB) {
             if constexpr (RESIDUAL) { bulk_store(a.dres + t0 * (long long)d, sbase + a.off_r, RB * rrow); issued = true; }
-          } else if (has_out) {
-            TO* o = reinterpret_cast<TO*>(a.dout) + (t0 + lane) * a.ldo;
-            if (!out_contig) { bulk_store(o, sbase + a.off_out + lane * yrow, yrow); issued = true; }
-            else if (lane == 0) { bulk_store(o, sbase + a.off_out, RB * yrow); issued = true; }
           }
           if (issued) { bulk_commit(); bulk_wait_read(); }
         }
@@ -209,7 +206,9 @@ __global__ void __launch_bounds__(THREADS, 1) ln_shift_bwd_stream_kernel(const L
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
     uint8_t* rr = sb + a.off_r + (size_t)row * d * 4;
-    uint8_t* orow = sb + a.off_out + (size_t)row * d * sizeof(TO);
+    // the low-precision copy / dx goes straight to global memory (8-byte stores, 256 B contiguous per warp): keeping it
+    // out of the stage makes room for one more stage of loads in flight (DRAM latency under load is what starves the ring)
+    TO* orow = reinterpret_cast<TO*>(a.dout) + t * a.ldo;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       const int c = ch * 128 + lane * 4;
@@ -237,9 +236,9 @@ __global__ void __launch_bounds__(THREADS, 1) ln_shift_bwd_stream_kernel(const L
 #pragma unroll
           for (int i = 0; i < 4; ++i) { r[i] += o[i]; cs_acc[ch][i] += r[i]; }
           st4<float>(rr + c * 4, r);
-          if (has_out) st4<TO>(orow + c * sizeof(TO), r);
+          if (has_out) st4<TO>(reinterpret_cast<uint8_t*>(orow + c), r);
         } else {
-          st4<TO>(orow + c * sizeof(TO), o);
+          st4<TO>(reinterpret_cast<uint8_t*>(orow + c), o);
         }
       }
     }
@@ -277,8 +276,8 @@ int launch_stream(const LnStreamArgs& a, int smem_bytes, cudaStream_t s) {
   const int grid = (int)(nchunks < pg_num_sms() ? nchunks : pg_num_sms());
   static bool attr_set = false;               // per (TI, TO, RESIDUAL): both NCH variants get the full opt-in once
   if (!attr_set) {
-    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 4, RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 8, RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 4, RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 8, RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;
   }
   if (a.d <= 512) ln_shift_bwd_stream_kernel<TI, TO, 4, RESIDUAL><<<grid, THREADS, smem_bytes, s>>>(a);
@@ -309,11 +308,10 @@ int ln_shift_bwd_stream_launch(const void* dy, long long lddy, int act_dtype, co
   int off = up(RB * d * si);
   a.off_dy = off; off += up((RB + 1) * d * so);
   a.off_r = off; if (residual) off += up(RB * d * 4);
-  a.off_out = off; if (dout) off += up(RB * d * so);
+  a.off_out = off;                               // (no longer staged: written directly)
   a.off_stat = off; off += 128;
   a.stage_bytes = off;
-  const int budget = 200 * 1024;
-  a.stages = budget / a.stage_bytes;
+  a.stages = SMEM_BUDGET / a.stage_bytes;
   if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
   if (a.stages < 2) return 1;
   const int smem_bytes = a.stages * a.stage_bytes;
