@@ -171,21 +171,7 @@ def run_reference_arm(args, cfgd):
     print(json.dumps(line), flush=True)
 
 
-def time_dominant_gemm(eng, iters=20):
-    """The dominant kernel: the tcgen05 GEMM on its largest single shape of this config (FF proj_in forward,
-    [T, d] x [d, 8d] with the GLU epilogue), timed alone with CUDA events on the launching stream."""
-    from progen_b200 import lib as L
-    from progen_b200.engine import P
-    i = next(j for j, k in enumerate(eng.kinds) if k == 'glu') if 'glu' in eng.kinds else None
-    if i is None:
-        return None
-    s = eng.lay[i]
-    f = P + f'ff{i}/~/'
-    hid, d, T = eng.hid, eng.d, eng.T
-
-    def launch():
-        eng.fwd_gemm(s['y2'], d, eng.W(f + 'linear', 'w'), 2 * hid, s['hact'], epi=L.EPI_GLU, ldo=hid, out2=s['u'], ldo2=2 * hid,
-                     bias=eng.Pf(f + 'linear', 'b'))
+def _time_launch(launch, iters):
     for _ in range(3):
         launch()
     torch.cuda.synchronize()
@@ -195,20 +181,41 @@ def time_dominant_gemm(eng, iters=20):
         launch()
     b.record()
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / iters
-    flops = 2.0 * T * d * 2 * hid
-    return dict(kernel='gemm_tc2_kernel<MN-major B, EPI_GLU, bf16> (CTA-pair tcgen05, FF proj_in fwd)', shape=[T, 2 * hid, d], ms=ms,
-                tflops=flops / ms / 1e9)
+    return a.elapsed_time(b) / iters
 
 
-def dominant_kernel_traffic(config, batch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-    `ncu --set full` capture of scripts/dominant_gemm.py (profiles/r01_dominant_kernel.json); null for any other shape."""
+def time_dominant_gemm(eng, iters=20, which='wgrad'):
+    """The dominant kernel of the step, timed alone with CUDA events on the launching stream.  By share of the step
+    (profiles/r01_launch_shares_step35ms.txt) that is the CTA-pair tcgen05 GEMM in its weight-gradient form (14.6 %); its
+    largest launch is dW_in += y2^T du of the feed-forward, [d x 8d x T].  `which='glu'` times the largest single launch of
+    the forward instead (FF proj_in + GLU epilogue, [T x 8d x d]) — reported beside it."""
+    from progen_b200 import lib as L
+    from progen_b200.engine import P
+    i = next(j for j, k in enumerate(eng.kinds) if k == 'glu') if 'glu' in eng.kinds else None
+    if i is None:
+        return None
+    s = eng.lay[i]
+    f = P + f'ff{i}/~/'
+    hid, d, T = eng.hid, eng.d, eng.T
+    if which == 'wgrad':
+        ms = _time_launch(lambda: eng.wgrad_gemm(s['y2'], d, eng.du, 2 * hid, eng.G(f + 'linear', 'w')), iters)
+        return dict(key='wgrad_ffin', kernel='gemm_tc2_kernel<MN-major A, MN-major B, EPI_ACCUM, fp32> (CTA-pair tcgen05, FF proj_in '
+                                             'weight gradient, split-K + TMA reduce-add)', shape=[d, 2 * hid, T], ms=ms,
+                    tflops=2.0 * T * d * 2 * hid / ms / 1e9)
+    ms = _time_launch(lambda: eng.fwd_gemm(s['y2'], d, eng.W(f + 'linear', 'w'), 2 * hid, s['hact'], epi=L.EPI_GLU, ldo=hid,
+                                           out2=s['u'], ldo2=2 * hid, bias=eng.Pf(f + 'linear', 'b')), iters)
+    return dict(key='ffin_glu', kernel='gemm_tc2_kernel<K-major A, MN-major B, EPI_GLU, bf16> (CTA-pair tcgen05, FF proj_in fwd)',
+                shape=[T, 2 * hid, d], ms=ms, tflops=2.0 * T * d * 2 * hid / ms / 1e9)
+
+
+def dominant_kernel_traffic(config, batch, key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of kernel `key`, from the committed `ncu --set full`
+    capture of scripts/dominant_gemm.py (profiles/r01_dominant_kernel.json); null for any other shape."""
     p = os.path.join(ROOT, 'profiles', 'r01_dominant_kernel.json')
     try:
         j = json.load(open(p))
         if j.get('config') == config and j.get('batch') == batch:
-            return j['dram_bytes_per_launch']
+            return j['kernels'][key]['dram_bytes_per_launch']
     except Exception:
         pass
     return None
@@ -321,15 +328,20 @@ def main():
         train_flops = 3.0 * fwd_flops_per_token(kw)
         achieved = tps * train_flops / 1e12 / world
         dom = time_dominant_gemm(eng) if not args.fp32 else None
+        glu = time_dominant_gemm(eng, which='glu') if not args.fp32 else None
         whole_step = dict(achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s', frac=achieved / peaks['sustained'],
                           peak_source=peaks['source'] + ', sustained figure (kernels timed inside a long step)',
                           definition='whole step: tokens/s x 3 x F_fwd (SURVEY 8d, %.2f MFLOP/token train) per GPU' % (train_flops / 1e6))
         if dom:
             # the dominant kernel, timed alone with CUDA events just above: algorithmic FLOPs of one launch / its duration
             roofline = dict(bound='tensor', achieved=dom['tflops'], peak=peaks['burst'], unit='TFLOP/s',
-                            frac=dom['tflops'] / peaks['burst'], traffic=dominant_kernel_traffic(args.config, B),
+                            frac=dom['tflops'] / peaks['burst'], traffic=dominant_kernel_traffic(args.config, B, dom['key']),
                             kernel=dom['kernel'], shape=dom['shape'], ms=dom['ms'],
                             peak_source=peaks['source'] + ', burst figure (kernel timed alone)', whole_step=whole_step)
+            if glu:
+                roofline['largest_forward_launch'] = dict(kernel=glu['kernel'], shape=glu['shape'], ms=glu['ms'], achieved=glu['tflops'],
+                                                          frac=glu['tflops'] / peaks['burst'],
+                                                          traffic=dominant_kernel_traffic(args.config, B, glu['key']))
         else:
             roofline = dict(bound='tensor', traffic=None, **whole_step)
         line = dict(metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=world, steps=args.steps, warmup=args.warmup,

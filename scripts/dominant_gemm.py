@@ -1,4 +1,5 @@
-"""Launch only bench.py's dominant kernel (FF proj_in forward GEMM with the GLU epilogue, config-2 shape) a few times.
+"""Launch only bench.py's dominant kernel (KERNEL=wgrad: FF proj_in weight gradient, default; KERNEL=glu: FF proj_in
+forward GEMM with the GLU epilogue; config-2 shapes) a few times.
 
 Meant to sit under `ncu --set full -k regex:gemm_tc -c 1 --launch-skip N` so the capture holds exactly the kernel whose
 roofline bench.py reports; prints the CUDA-event timing when run bare."""
@@ -27,7 +28,7 @@ def main():
     tr.step_resident(global_batch=B)           # populates the saved activations the GEMM reads
     torch.cuda.synchronize()
     torch.cuda.profiler.start()                # ncu --profile-from-start off: only the launches below are visible
-    res = bench.time_dominant_gemm(eng, iters=int(os.environ.get('ITERS', '5')))
+    res = bench.time_dominant_gemm(eng, iters=int(os.environ.get('ITERS', '5')), which=os.environ.get('KERNEL', 'wgrad'))
     torch.cuda.profiler.stop()
     print('DOMINANT ' + json.dumps(res))
 
