@@ -276,8 +276,13 @@ def main():
     graph_nodes = 0
     if world == 1 and os.environ.get('PROGEN_BENCH_GRAPH', '1') != '0':
         c0 = L.load().progen_launch_count()
-        tr.capture_graph(B)
-        graph_nodes = int(L.load().progen_launch_count() - c0)         # kernels of ours recorded per step
+        try:
+            tr.capture_graph(B)
+            graph_nodes = int(L.load().progen_launch_count() - c0)     # kernels of ours recorded per step
+        except Exception as e:                                          # same kernels, launched eagerly instead
+            print(f'[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); continuing with eager launches', file=sys.stderr)
+            tr._graph = None
+            torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = L.load().progen_launch_count()
