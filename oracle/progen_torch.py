@@ -120,10 +120,12 @@ def batch_loss(prm, data, cfg, operand_round=None):
     return cross_entropy(forward(prm, ids, cfg, operand_round), labels).mean()
 
 
-def loss_and_grads(params_np, data_np, cfg, dtype=torch.float64):
+def loss_and_grads(params_np, data_np, cfg, dtype=torch.float64, operand_round=None):
+    """`operand_round=bf16_round` (with dtype=float32) is the CPU emulation of a bf16-operand / fp32-accumulate engine:
+    autograd sends the gradients through the same casts, so the backward GEMM operands are rounded as well."""
     prm = to_torch(params_np, dtype, requires_grad=True)
     data = torch.as_tensor(data_np.astype('int64'))
-    loss = batch_loss(prm, data, cfg)
+    loss = batch_loss(prm, data, cfg, operand_round)
     loss.backward()
     grads = {m: {k: v.grad.numpy().copy() for k, v in d.items()} for m, d in prm.items()}
     return float(loss.detach()), grads

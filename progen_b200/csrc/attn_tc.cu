@@ -19,6 +19,7 @@
 
 // attn_tc_pair.cu
 int attn_fwd_pair_launch(const void* qkv, void* out, float* lse, int B, int seq_len, int window, int heads, cudaStream_t stream);
+int attn_fwd_ts_launch(const void* qkv, void* out, float* lse, int B, int seq_len, int window, int heads, cudaStream_t stream);
 
 namespace {
 
@@ -315,7 +316,10 @@ int progen_local_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int 
                              void* stream) {
   PG_CHECK_ARG(B > 0 && heads > 0 && dim_head == DH && window % 128 == 0 && seq_len % window == 0);
   PG_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0);
-  // two query tiles per CTA with independent softmax groups (attn_tc_pair.cu) when the window holds whole pairs
+  // round-2 kernel (P and O in tensor memory, attn_fwd_ts.cu) when the window holds whole pairs of query tiles
+  const int rc_ts = attn_fwd_ts_launch(qkv, out, lse, B, seq_len, window, heads, (cudaStream_t)stream);
+  if (rc_ts <= 0) return rc_ts;
+  // round-1 form: two query tiles per CTA with independent softmax groups (attn_tc_pair.cu)
   const int rc_pair = attn_fwd_pair_launch(qkv, out, lse, B, seq_len, window, heads, (cudaStream_t)stream);
   if (rc_pair <= 0) return rc_pair;
   const long long T = (long long)B * seq_len;

@@ -348,7 +348,9 @@ __global__ void ce_fwd_bwd_kernel(const TL* __restrict__ logits, const int* __re
       for (int i = 0; i < 4; ++i) se += expf(v[i] - mx);
     }
     se = warp_sum(se);
-    const int lab = labels[t];
+    // out-of-range labels are clamped like the token ids in embed_fwd / embed_bwd (jnp indexing clamps); byte 0xFF + 1 = 256
+    // with V = 256 is reachable from real data (data.py tokenizer) and must not read past the logits row
+    const int lab = min(max(labels[t], 0), V - 1);
     const float wt = w[t];
     const float lse = mx + logf(se);
     if (lane == 0) block_loss += wt * (lse - to_f32(lr[lab]));

@@ -94,8 +94,9 @@ class Engine:
         self.act_dt = L.BF16 if self.mp else L.F32
         self.backend = L.BACKEND_TC if self.mp else L.BACKEND_SIMT
         self.kinds = layer_kinds(cfg['depth'], cfg['global_mlp_depth'], cfg['ff_glu'])
-        # tensor-core attention kernel needs bf16, dim_head 64 and 64-aligned windows; other shapes use the CUDA-core kernel
-        self.attn_tc = self.mp and cfg['dim_head'] == 64 and cfg['window_size'] % 64 == 0
+        # tensor-core attention kernels: bf16, dim_head 64, 64-aligned windows (checked below — no silent CUDA-core fallback);
+        # the fp32 engine (mixed_precision=False) runs the exact CUDA-core kernels
+        self.attn_tc = self.mp
         import os
         self.attn_fwd_kind = os.environ.get('PROGEN_ATTN_FWD', 'tcgen05')
         self.attn_bwd_kind = os.environ.get('PROGEN_ATTN_BWD', 'tcgen05')
@@ -112,6 +113,14 @@ class Engine:
             raise L.ProgenError('dim_head must be one of 16/32/64/128')
         if d % 8 or self.I % 8 or self.V % 8:
             raise L.ProgenError('dim, heads*dim_head and num_tokens must be multiples of 8')
+        if self.V > 384:
+            raise L.ProgenError('num_tokens > 384 is not supported (embed_bwd keeps num_tokens x 32 fp32 bins in 48 KB of shared memory)')
+        if self.mp and self.dh != 64:
+            # the tensor-core attention kernels are built for dim_head 64; running another head size on the CUDA-core
+            # kernel under mixed_precision would be a silent 10x slowdown, so it is refused (mixed_precision=False runs it)
+            raise L.ProgenError(f'mixed_precision needs dim_head == 64 (got {self.dh}); use mixed_precision=False for other head sizes')
+        if self.mp and w % 64:
+            raise L.ProgenError(f'mixed_precision needs window_size % 64 == 0 (got {w}); use mixed_precision=False')
         if self.mp:
             bad = [k for k, v in dict(dim=d, inner=self.I, seq_len=n, num_tokens=self.V).items() if v % 64]
             if bad:
@@ -133,6 +142,7 @@ class Engine:
         self.rot_sin = torch.tensor(np.sin(ang), **f32).contiguous()
         self.rot_cos = torch.tensor(np.cos(ang), **f32).contiguous()
         self.B = 0
+        self.loss = torch.zeros(1, device=self.dev)       # exists before the first batch: a rank without rows still reports 0
         self.loaded_token = None
         self.on_layer_grads = None        # optional callback(layer_index) fired when a layer's weight gradients are final
         self.lib = L.load()
@@ -236,7 +246,6 @@ class Engine:
         self.logits = F(T, self.V)
         self.dlogits = A(T, self.V)
         self.ce_w = F(T)
-        self.loss = torch.zeros(1, device=dev)
         # backward temporaries (shared by all layers)
         self.dres = F(T, d)
         self.dres_lp = A(T, d) if self.mp else self.dres
@@ -339,8 +348,9 @@ class Engine:
 
     def attn_fwd(self, qkv, out, lse):
         if self.attn_tc:
-            # two tensor-core forwards: `mma` (mma.sync flash kernel, currently the faster one) and `tcgen05` (TMA + tcgen05.mma +
-            # TMEM, attn_tc.cu; needs window % 128 == 0).  PROGEN_ATTN_FWD selects; default = mma.
+            # two tensor-core forwards: `tcgen05` (default: TMA + tcgen05.mma + TMEM, attn_fwd_ts.cu / attn_tc_pair.cu /
+            # attn_tc.cu by window size; needs window % 128 == 0) and `mma` (mma.sync flash kernel, any window % 64 == 0).
+            # PROGEN_ATTN_FWD selects.
             if self.attn_fwd_kind == 'tcgen05':
                 L.check(self.lib.progen_local_attn_fwd_tc(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), self.B, self.n, self.w,
                                                           self.h, self.dh, L.stream()), 'local_attn_fwd_tc')

@@ -31,23 +31,39 @@ class Trainer:
         # cuda_graph=True: after two eager steps of one batch shape the step is captured and replayed from then on
         self._auto_graph, self._eager_key, self._eager_run = bool(cuda_graph), None, 0
         self._bucket, self._bucket_layers = None, max(1, int(os.environ.get('PROGEN_DDP_BUCKET_LAYERS', '3')))
-        if self.world > 1:
+        # Gradient exchange (world > 1).  Default: ONE SUM all-reduce of the whole flat buffer after the backward pass, on
+        # the compute stream, inside the captured CUDA graph.  Round 1 overlapped per-layer buckets with the backward pass:
+        # the NCCL kernels then hold SMs that the persistent one-CTA-per-SM kernels count on, and every such kernel ends
+        # late by the wait (2.2 ms per step at 8 GPUs for 0.5 ms of transfer).  PROGEN_DDP_OVERLAP=1 restores that mode
+        # (eager launches only) for models whose gradient is large enough to make the transfer itself matter.
+        self.overlap = os.environ.get('PROGEN_DDP_OVERLAP', '0') == '1'
+        self.skip_allreduce = False                       # bench.py: "step without the exchange" for comm_exposed_ms
+        if self.world > 1 and self.overlap:
             # overlap: a layer's weight gradients are all-reduced (async, NCCL's stream) as soon as its backward is done
             self.eng.on_layer_grads = self._reduce_layer
         if optim_state is not None:
             self.load_optim_state(optim_state)
 
     # ---- one micro-step of train.py:186-190
-    def step(self, data, sync_loss=False):
-        """data: this rank's rows, (b, n+1) integers.  Returns the device scalar loss (global mean when sync_loss)."""
-        gb = data.shape[0] * self.world if self.world > 1 else data.shape[0]
-        self._drop_graph_unless(data.shape[0])
-        if self._graph is not None and self._graph_key == (data.shape[0], gb):
+    def step(self, data, sync_loss=False, global_batch=None):
+        """data: this rank's rows, (b, n+1) integers; `global_batch` = rows of the UNSHARDED batch (utils.py:83-91: the
+        masked mean divides by the real row count, so ragged shards — 5 rows over 2 ranks = 3 + 2, or ranks with no rows
+        at all — must all scale by 1/5).  Without it the shards are assumed equal.  Returns the device scalar loss
+        (global mean when sync_loss)."""
+        rows = data.shape[0]
+        gb = int(global_batch) if global_batch is not None else (rows * self.world if self.world > 1 else rows)
+        if rows == 0:
+            # a rank without rows (batch smaller than the world): zero contribution, but every collective is joined
+            self.eng.grads.zero_()
+            self.eng.loss.zero_()
+            return self._update(sync_loss)
+        self._drop_graph_unless(rows)
+        if self._graph is not None and self._graph_key == (rows, gb):
             self.eng.load_batch(data)                      # H2D copies stay outside the graph
-            return self._replay()
+            return self._replay(sync_loss)
         self.eng.loss_and_grad(data, global_batch=gb)
         loss = self._update(sync_loss)
-        if self._auto_graph and self.world == 1:
+        if self._auto_graph and not self.overlap:
             key = (data.shape[0], gb)
             self._eager_run = self._eager_run + 1 if key == self._eager_key else 1
             self._eager_key = key
@@ -61,31 +77,45 @@ class Trainer:
         gb = global_batch or self.eng.B * self.world
         self._drop_graph_unless(self.eng.B)
         if self._graph is not None and self._graph_key == (self.eng.B, gb):
-            return self._replay()
+            return self._replay(sync_loss)
         self.eng.step_device(gb)
         return self._update(sync_loss)
 
-    # ---- CUDA graph of the whole step (single GPU): forward, loss, backward, norm, AdamW, masked copies = ~285 launches
-    def capture_graph(self, batch_rows, global_batch=None):
+    # ---- CUDA graph of the whole step: forward, loss, backward, (gradient all-reduce), norm, AdamW, masked copies
+    def capture_graph(self, batch_rows, global_batch=None, install=True):
         """Capture one training step for batches of `batch_rows` rows into a CUDA graph; later `step` / `step_resident`
         calls with that shape replay it.  The step-dependent optimizer scalars live on the device
-        (`progen_adamw_step_dev`), so the graph is identical for every step.  Call after at least one eager step of the
-        same shape (kernel attributes, tensor maps and buffers must exist before capture)."""
-        if self.world > 1:
-            raise L.ProgenError('capture_graph: single-GPU only (the NCCL path overlaps its all-reduces eagerly)')
+        (`progen_adamw_step_dev`), so the graph is identical for every step.  Under data parallelism the NCCL all-reduce
+        of the gradient buffer is part of the graph (issued on the capture stream between backward and the norm).  Call
+        after at least one eager step of the same shape (kernel attributes, tensor maps, buffers and the NCCL communicator
+        must exist before capture).  `install=False` returns the graph without making it the one `step` replays."""
+        if self.world > 1 and self.overlap:
+            raise L.ProgenError('capture_graph: PROGEN_DDP_OVERLAP=1 launches its bucketed all-reduces eagerly')
         eng = self.eng
         eng.ensure_batch(batch_rows)
-        gb = global_batch or batch_rows
-        st = torch.zeros(4, dtype=torch.int64, device=eng.dev)          # AdamDevState: count | bc1, bc2 | emit, pad
-        st[0] = self.count
-        self._adam_state = st
+        gb = global_batch or batch_rows * self.world
+        if self._adam_state is None:
+            self._adam_state = torch.zeros(4, dtype=torch.int64, device=eng.dev)   # AdamDevState: count | bc1, bc2 | emit, pad
+        self._adam_state[0] = self.count
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             eng.step_device(gb)
+            self._allreduce_grads()
             self._update_captured()
-        self._graph, self._graph_key, self._graph_epoch = g, (batch_rows, gb), getattr(eng, 'alloc_epoch', 0)
+        if install:
+            self._graph, self._graph_key, self._graph_epoch = g, (batch_rows, gb), getattr(eng, 'alloc_epoch', 0)
         return g
+
+    def _allreduce_grads(self):
+        """SUM of the per-rank gradients (each already scaled by 1/global_rows): the reference's pmap mean, utils.py:78-91"""
+        if self.world <= 1 or self.skip_allreduce:
+            return
+        import torch.distributed as dist
+        if self.overlap:
+            self._finish_allreduce()
+        else:
+            dist.all_reduce(self.eng.grads, op=dist.ReduceOp.SUM)
 
     def _update_captured(self):
         eng, lib, st = self.eng, L.load(), L.stream()
@@ -103,9 +133,11 @@ class Trainer:
                                         getattr(self.eng, 'alloc_epoch', 0) != self._graph_epoch):
             self._graph, self._graph_key = None, None      # (model.apply / sampling with another batch size re-allocates too)
 
-    def _replay(self):
+    def _replay(self, sync_loss=False):
         self._graph.replay()
         self.count += 1
+        if sync_loss and self.world > 1:
+            PAR.allreduce_scalar_(self.eng.loss)           # logged loss only; the next replay zeroes it again
         return self.eng.loss
 
     def _reduce_layer(self, i):
@@ -144,7 +176,7 @@ class Trainer:
     def _update(self, sync_loss):
         eng, lib, st = self.eng, L.load(), L.stream()
         if self.world > 1:
-            self._finish_allreduce()
+            self._allreduce_grads()
             if sync_loss:
                 PAR.allreduce_scalar_(eng.loss)
         self.count += 1

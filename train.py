@@ -57,9 +57,20 @@ def main(seed, batch_size, grad_accum_every, learning_rate, weight_decay, data_p
     reset_checkpoint, get_last_checkpoint, save_checkpoint = get_checkpoint_fns(checkpoint_path)
     if new and rank == 0:
         if not confirm('are you sure you want to clear all your checkpoints and restart training?'):
+            if world > 1:
+                import torch.distributed as dist
+                dist.destroy_process_group()
             exit()
         reset_checkpoint()
-    last_checkpoint = get_last_checkpoint()
+    if world > 1:
+        # every rank must start from the SAME state: rank 0 (which may just have cleared the folder) reads the checkpoint
+        # and broadcasts the package; without this the other ranks could load the old files before rank 0 removes them
+        import torch.distributed as dist
+        box = [get_last_checkpoint() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        last_checkpoint = box[0]
+    else:
+        last_checkpoint = get_last_checkpoint()
     if not exists(last_checkpoint):
         cfg_file = Path(config_path) / f'{model_name}.toml'
         assert cfg_file.exists(), f'path to your model config {str(cfg_file)} does not exist'
@@ -74,7 +85,7 @@ def main(seed, batch_size, grad_accum_every, learning_rate, weight_decay, data_p
         params, optim_state, start_seq_index = model.init(seed), None, 0
     trainer = model.trainer(params, learning_rate=learning_rate, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
                             grad_accum_every=grad_accum_every, optim_state=optim_state, data_parallel=data_parallel,
-                            cuda_graph=cuda_graph and world == 1)
+                            cuda_graph=cuda_graph)
     seq_len = model_kwargs['seq_len']                           # the --seq_len flag is dead in the reference too (train.py:137)
     num_params = model.engine.num_params
 
@@ -114,7 +125,7 @@ def main(seed, batch_size, grad_accum_every, learning_rate, weight_decay, data_p
             except StopIteration:
                 return
             local = PAR.shard_batch(data) if world > 1 else data
-            loss = trainer.step(local, sync_loss=True)
+            loss = trainer.step(local, sync_loss=True, global_batch=data.shape[0])
             tokens += data.shape[0] * seq_len
         if rank == 0:
             print(f'loss: {loss.item()}')
