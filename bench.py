@@ -184,40 +184,63 @@ def _time_launch(launch, iters):
     return a.elapsed_time(b) / iters
 
 
-def time_dominant_gemm(eng, iters=20, which='wgrad'):
-    """The dominant kernel of the step, timed alone with CUDA events on the launching stream.  By share of the step
-    (profiles/r01_launch_shares_step35ms.txt) that is the CTA-pair tcgen05 GEMM in its weight-gradient form (14.6 %); its
-    largest launch is dW_in += y2^T du of the feed-forward, [d x 8d x T].  `which='glu'` times the largest single launch of
-    the forward instead (FF proj_in + GLU epilogue, [T x 8d x d]) — reported beside it."""
+def attn_fwd_flops_per_token(kw):
+    """4 I (w + (w + 1) / 2) per token per layer — the causal keys actually visible, two contractions"""
+    return 4.0 * kw['heads'] * kw['dim_head'] * (kw['window_size'] + (kw['window_size'] + 1) / 2)
+
+
+def time_step_kernels(eng, kw, iters=20):
+    """The kernels that carry the step, each timed ALONE with CUDA events on the launching stream (same buffers and shapes
+    as inside the step), with the number of launches of that shape per step and its algorithmic FLOPs (no
+    recompute credit — the attention backward is charged 2x the forward's FLOPs although its two kernels execute 3.5x).
+    The caller picks the largest share of the step as the `roofline` kernel and lists the rest beside it."""
     from progen_b200 import lib as L
     from progen_b200.engine import P
-    i = next(j for j, k in enumerate(eng.kinds) if k == 'glu') if 'glu' in eng.kinds else None
-    if i is None:
-        return None
-    s = eng.lay[i]
-    f = P + f'ff{i}/~/'
-    hid, d, T = eng.hid, eng.d, eng.T
-    if which == 'wgrad':
+    out = []
+    T, d, I, hid = eng.T, eng.d, eng.I, eng.hid
+    nl = len(eng.kinds)
+    s0 = eng.lay[0]
+    if eng.attn_tc:
+        fa = attn_fwd_flops_per_token(kw) * T
+        ms = _time_launch(lambda: eng.attn_fwd(s0['qkv'], s0['att'], s0['lse']), iters)
+        out.append(dict(key='attn_fwd', kernel='sliding-window attention forward (tcgen05, P and O in TMEM)', per_step=nl, ms=ms,
+                        flops=fa, shape=[eng.B, eng.h, eng.n, eng.w]))
+        ms = _time_launch(lambda: eng.attn_bwd(s0['qkv'], s0['att'], eng.datt, s0['lse'], eng.dqkv), iters)
+        out.append(dict(key='attn_bwd', kernel='sliding-window attention backward (dQ kernel + dK/dV kernel, tcgen05)', per_step=nl,
+                        ms=ms, flops=2.0 * fa, shape=[eng.B, eng.h, eng.n, eng.w]))
+    i = next((j for j, k in enumerate(eng.kinds) if k == 'glu'), None)
+    if i is not None:
+        s = eng.lay[i]
+        f = P + f'ff{i}/~/'
+        n_glu = sum(1 for k in eng.kinds if k == 'glu')
         ms = _time_launch(lambda: eng.wgrad_gemm(s['y2'], d, eng.du, 2 * hid, eng.G(f + 'linear', 'w')), iters)
-        return dict(key='wgrad_ffin', kernel='gemm_tc2_kernel<MN-major A, MN-major B, EPI_ACCUM, fp32> (CTA-pair tcgen05, FF proj_in '
-                                             'weight gradient, split-K + TMA reduce-add)', shape=[d, 2 * hid, T], ms=ms,
-                    tflops=2.0 * T * d * 2 * hid / ms / 1e9)
-    ms = _time_launch(lambda: eng.fwd_gemm(s['y2'], d, eng.W(f + 'linear', 'w'), 2 * hid, s['hact'], epi=L.EPI_GLU, ldo=hid,
-                                           out2=s['u'], ldo2=2 * hid, bias=eng.Pf(f + 'linear', 'b')), iters)
-    return dict(key='ffin_glu', kernel='gemm_tc2_kernel<K-major A, MN-major B, EPI_GLU, bf16> (CTA-pair tcgen05, FF proj_in fwd)',
-                shape=[T, 2 * hid, d], ms=ms, tflops=2.0 * T * d * 2 * hid / ms / 1e9)
+        out.append(dict(key='wgrad_ffin', kernel='gemm_tc2_kernel<MN-major A, MN-major B, EPI_ACCUM, fp32> (CTA-pair tcgen05, FF proj_in '
+                                                 'weight gradient, split-K + TMA reduce-add)', per_step=n_glu, ms=ms,
+                        flops=2.0 * T * d * 2 * hid, shape=[d, 2 * hid, T]))
+        ms = _time_launch(lambda: eng.fwd_gemm(s['y2'], d, eng.W(f + 'linear', 'w'), 2 * hid, s['hact'], epi=L.EPI_GLU, ldo=hid,
+                                               out2=s['u'], ldo2=2 * hid, bias=eng.Pf(f + 'linear', 'b')), iters)
+        out.append(dict(key='ffin_glu', kernel='gemm_tc2_kernel<K-major A, MN-major B, EPI_GLU, bf16> (CTA-pair tcgen05, FF proj_in fwd)',
+                        per_step=n_glu, ms=ms, flops=2.0 * T * d * 2 * hid, shape=[T, 2 * hid, d]))
+        ms = _time_launch(lambda: eng.dgrad_gemm(eng.dres_lp, d, eng.W(f + 'linear_1', 'w'), hid, eng.du, epi=L.EPI_GLU_BWD,
+                                                 ldo=2 * hid, aux=s['u'], ldaux=2 * hid), iters)
+        out.append(dict(key='ffout_dgrad_glu_bwd', kernel='gemm_tc2_kernel<K-major, K-major, EPI_GLU_BWD, bf16> (FF proj_out dgrad + GLU backward)',
+                        per_step=n_glu, ms=ms, flops=2.0 * T * d * hid, shape=[T, hid, d]))
+    for o in out:
+        o['tflops'] = o['flops'] / o['ms'] / 1e9
+        o['step_ms'] = o['ms'] * o['per_step']
+    return out
 
 
 def dominant_kernel_traffic(config, batch, key):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of kernel `key`, from the committed `ncu --set full`
-    capture of scripts/dominant_gemm.py (profiles/r01_dominant_kernel.json); null for any other shape."""
-    p = os.path.join(ROOT, 'profiles', 'r01_dominant_kernel.json')
-    try:
-        j = json.load(open(p))
-        if j.get('config') == config and j.get('batch') == batch:
-            return j['kernels'][key]['dram_bytes_per_launch']
-    except Exception:
-        pass
+    captures (profiles/r02_dominant_kernel.json, else round 1's file); null for any other shape."""
+    for name in ('r02_dominant_kernel.json', 'r01_dominant_kernel.json'):
+        try:
+            j = json.load(open(os.path.join(ROOT, 'profiles', name)))
+            if j.get('config') == config and j.get('batch') == batch and key in j['kernels']:
+                return j['kernels'][key]['dram_bytes_per_launch']
+        except Exception:
+            pass
     return None
 
 
@@ -273,16 +296,25 @@ def main():
         tr.step_resident(global_batch=B * world)
     # single GPU: the whole step (forward, loss, backward, norm, AdamW) is captured ONCE into a CUDA graph after the eager
     # warm-up and replayed by the same Trainer.step / step_resident calls (PROGEN_BENCH_GRAPH=0 keeps eager launches)
+    # The whole step (forward, loss, backward, gradient all-reduce, norm, AdamW) is captured ONCE into a CUDA graph after the
+    # eager warm-up and replayed by the same Trainer.step / step_resident calls — at N > 1 the NCCL all-reduce is part of the
+    # graph (PROGEN_BENCH_GRAPH=0 keeps eager launches; PROGEN_DDP_OVERLAP=1 is the round-1 bucketed overlap, eager only)
     graph_nodes = 0
-    if world == 1 and os.environ.get('PROGEN_BENCH_GRAPH', '1') != '0':
+    graph_ok = torch.ones(1, device='cuda')
+    if os.environ.get('PROGEN_BENCH_GRAPH', '1') != '0' and not tr.overlap:
         c0 = L.load().progen_launch_count()
         try:
-            tr.capture_graph(B)
+            tr.capture_graph(B, B * world)
             graph_nodes = int(L.load().progen_launch_count() - c0)     # kernels of ours recorded per step
         except Exception as e:                                          # same kernels, launched eagerly instead
-            print(f'[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); continuing with eager launches', file=sys.stderr)
+            print(f'[bench] rank {rank}: CUDA-graph capture failed ({type(e).__name__}: {e}); continuing with eager launches', file=sys.stderr)
             tr._graph = None
+            graph_ok.zero_()
             torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(graph_ok, op=dist.ReduceOp.MIN)             # all ranks replay, or none does (the collectives must pair up)
+            if graph_ok.item() == 0:
+                tr._graph, graph_nodes = None, 0
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = L.load().progen_launch_count()
@@ -302,7 +334,11 @@ def main():
     if graph_nodes:
         launches = graph_nodes * args.steps            # replayed graph: the host-side counter only sees the capture
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    per_rank_ms = [float(ms.item()) / args.steps]
     if world > 1:
+        gathered = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(gathered, ms)
+        per_rank_ms = [float(g.item()) / args.steps for g in gathered]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clocks = sampler.stop() if sampler else None
@@ -325,6 +361,34 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms2.item())
 
+    # ---------------- exposed communication: the same K steps with the gradient exchange removed (same launch mode, same box);
+    # the ranks no longer agree afterwards, so this runs last and nothing is reported from its state
+    comm = None
+    if world > 1:
+        tr.skip_allreduce = True
+        try:
+            if tr._graph is not None:
+                tr._graph = None
+                tr.capture_graph(B, B * world)
+            for i in range(2):
+                tr.step_resident(global_batch=B * world)
+            barrier()
+            e0.record()
+            for i in range(args.warmup, total):
+                eng.tok.copy_(dev_batches[i][:, :-1].reshape(-1)); eng.labels.copy_(dev_batches[i][:, 1:].reshape(-1))
+                tr.step_resident(global_batch=B * world)
+            e1.record()
+            barrier()
+            ms3 = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+            comm = dict(step_ms_without_exchange=float(ms3.item()) / args.steps,
+                        comm_exposed_ms=ms_total / args.steps - float(ms3.item()) / args.steps,
+                        grad_bytes=int(eng.n_params_padded) * 4, mode='bucketed overlap (eager)' if tr.overlap else
+                        'one fp32 SUM all-reduce after backward, inside the step graph' if graph_nodes else 'one fp32 SUM all-reduce after backward (eager)')
+        except Exception as e:
+            print(f'[bench] rank {rank}: comm_exposed measurement failed ({type(e).__name__}: {e})', file=sys.stderr)
+        tr.skip_allreduce = False
+
     tokens_per_step = B * n * world
     tps = tokens_per_step * args.steps / (ms_total / 1e3)
     tps_e2e = tokens_per_step * args.steps / (ms_e2e / 1e3)
@@ -332,21 +396,24 @@ def main():
         peaks = measured_peaks()
         train_flops = 3.0 * fwd_flops_per_token(kw)
         achieved = tps * train_flops / 1e12 / world
-        dom = time_dominant_gemm(eng) if not args.fp32 else None
-        glu = time_dominant_gemm(eng, which='glu') if not args.fp32 else None
+        kernels = time_step_kernels(eng, kw) if not args.fp32 else []
         whole_step = dict(achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s', frac=achieved / peaks['sustained'],
                           peak_source=peaks['source'] + ', sustained figure (kernels timed inside a long step)',
                           definition='whole step: tokens/s x 3 x F_fwd (SURVEY 8d, %.2f MFLOP/token train) per GPU' % (train_flops / 1e6))
-        if dom:
-            # the dominant kernel, timed alone with CUDA events just above: algorithmic FLOPs of one launch / its duration
+        if kernels:
+            # the dominant kernel = the (symbol, shape) with the largest share of the step; timed alone with CUDA events just
+            # above: algorithmic FLOPs of one launch / its duration, against the burst peak
+            step_ms = ms_total / args.steps
+            dom = max(kernels, key=lambda k: k['step_ms'])
             roofline = dict(bound='tensor', achieved=dom['tflops'], peak=peaks['burst'], unit='TFLOP/s',
                             frac=dom['tflops'] / peaks['burst'], traffic=dominant_kernel_traffic(args.config, B, dom['key']),
-                            kernel=dom['kernel'], shape=dom['shape'], ms=dom['ms'],
-                            peak_source=peaks['source'] + ', burst figure (kernel timed alone)', whole_step=whole_step)
-            if glu:
-                roofline['largest_forward_launch'] = dict(kernel=glu['kernel'], shape=glu['shape'], ms=glu['ms'], achieved=glu['tflops'],
-                                                          frac=glu['tflops'] / peaks['burst'],
-                                                          traffic=dominant_kernel_traffic(args.config, B, glu['key']))
+                            kernel=dom['kernel'], shape=dom['shape'], ms=dom['ms'], launches_per_step=dom['per_step'],
+                            share_of_step=dom['step_ms'] / step_ms,
+                            peak_source=peaks['source'] + ', burst figure (kernel timed alone)', whole_step=whole_step,
+                            others=[dict(key=k['key'], kernel=k['kernel'], shape=k['shape'], ms=k['ms'], launches_per_step=k['per_step'],
+                                         share_of_step=k['step_ms'] / step_ms, achieved=k['tflops'], frac=k['tflops'] / peaks['burst'],
+                                         traffic=dominant_kernel_traffic(args.config, B, k['key']))
+                                    for k in kernels if k is not dom])
         else:
             roofline = dict(bound='tensor', traffic=None, **whole_step)
         line = dict(metric='tokens_per_sec', value=tps, unit='tokens/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -355,11 +422,14 @@ def main():
                     config=dict(workload=cfgd['name'], global_batch=B * world, seq_len=n, parallelism=f'dp{world}',
                                 l2='activations (~%.1f GB/step) far exceed the 126 MB L2; no explicit flush' % (eng_bytes(eng) / 1e9),
                                 optimizer='clip_by_global_norm(0.5)+adamw(2e-4,wd=1e-3,mask)+apply_every(4), every step',
-                                launch='CUDA graph of the whole step (%d kernels), replayed' % graph_nodes if graph_nodes
+                                launch='CUDA graph of the whole step (%d kernels%s), replayed' % (graph_nodes, ' + the NCCL all-reduce' if world > 1 else '') if graph_nodes
                                        else 'eager launches'),
                     e2e=dict(value=tps_e2e, unit='tokens/s', h2d_bytes_per_step=B * (n + 1) * 4, d2h_bytes_per_step=4,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, final_loss=final_loss)
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, final_loss=final_loss,
+                    per_rank_ms_per_step=per_rank_ms)
+        if comm:
+            line['comm'] = comm
         if not args.no_cpu_baseline and world == 1:
             cores = cpu_threads()
             v, sec, rows, timed = cpu_port_tokens_per_sec(kw, steps=30, warmup=1, rows=1, budget_s=20.0)

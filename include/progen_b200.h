@@ -196,6 +196,40 @@ typedef struct progen_decode_t {
 
 int progen_decode_step(const progen_decode_t* model, int do_sample, void* stream);
 
+/* Whole-generation decode in ONE persistent cooperative kernel (csrc/decode_persist.cu): consumes positions
+ * pos0 .. pos0 + nsteps - 1 of B sequences in lock step (reference utils.py:106-135 per sequence; sample.py:66-71).
+ * `layers` is a DEVICE array of `depth` progen_decode_layer_t whose cache / state pointers are batch-major:
+ * kcache, vcache [B, n, inner]; shift1, shift2 [B, 2, d/2]; gn_hist [B, n, hid/2].  Sequence b keeps its prime before
+ * start[b]: position p+1 is sampled (seq[b][p+1] += id, quirk Q5) iff p+1 >= start[b].  grid_bar (one uint32) and att_count
+ * ([B * heads] int32) must be zero on entry.  B <= 64. */
+typedef struct progen_decode_run_t {
+  int32_t n, d, heads, dim_head, inner, window, hid, V, depth, wdtype, shift_tokens, top_k;
+  int32_t B, pos0, nsteps, _pad;
+  const float* embed;          /* [V, d] */
+  const float* lnf_scale;      /* [d] */
+  const void* whead_t;         /* [V, d] */
+  const float* bhead;          /* [V] */
+  const float* rot_sin;        /* [n, dim_head/2] */
+  const float* rot_cos;
+  const progen_decode_layer_t* layers;   /* device */
+  int32_t* seq;                /* [B, n] token ids; sampled ids are ADDED in place */
+  const int32_t* start;        /* [B] first sampled position of each sequence */
+  const float* noise;          /* [B, n, V] gumbel noise, or NULL for the greedy limit */
+  float* logits_all;           /* [B, n, V] every step's logits (may be NULL) */
+  float* x;                    /* [B, d] residual stream */
+  float* q;                    /* [B, inner] */
+  float* att;                  /* [B, inner] */
+  float* att_part;             /* [B, heads, ceil(2*window/32), dim_head + 2] partial (max, sum, out) per 32-key slice */
+  int32_t* att_count;          /* [B, heads] */
+  float* u;                    /* [B, hid] */
+  float* sg;                   /* [B, hid/2] */
+  float* pj;                   /* [B, hid/2] */
+  float* logits;               /* [B, V] */
+  uint32_t* grid_bar;          /* grid barrier counter */
+} progen_decode_run_t;
+
+int progen_decode_run(const progen_decode_run_t* run, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,8 +7,8 @@
 //
 //   * ONE TMEM pass: a thread loads its whole row of S (128 fp32) into registers, takes the maximum, exponentiates and
 //     packs in place (setmaxnreg gives the softmax warps 216 registers);
-//   * P never touches shared memory: it is written back to tensor memory over the first 64 columns of S as packed bf16
-//     (tcgen05.st) and the P V product reads its A operand from there (tcgen05.mma, A in TMEM);
+//   * P never touches shared memory: it is written to tensor memory as packed bf16 (tcgen05.st) and the P V product reads
+//     its A operand from there (tcgen05.mma, A in TMEM);
 //   * O accumulates in TMEM across the steps of an item (accumulate flag), it is rescaled (tcgen05.ld / st) only when a
 //     row maximum has grown by more than 2^8 since the maximum the exponents are currently taken against ("lazy
 //     rescale"; exact: l and O carry the same offset, the final O / l and the lse do not depend on it);
@@ -21,7 +21,11 @@
 //   warp 1, 3   : MMA issuer of group A, B:   S_g = Q_g K_j^T (128x128x64)   O_g (+)= P_g V_j (128x64x128, A from TMEM)
 //   warp 2      : TMEM allocator
 //   warps 4..7  : softmax group A (rows q0 .. q0+127), warps 8..11: group B (q0+128 ..)
-// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); P_g aliases S_g[0,64).
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
+// P has its own columns, so S_g(j+1) = Q_g K_{j+1}^T is issued the moment group g has READ S_g(j) into registers and runs
+// under the group's own exponentials: the softmax warps never wait for an MMA they have just requested (ncu on the first
+// version of this kernel, with P aliased over S: the two groups ran IN PHASE — both exponentiating, then both waiting for
+// P V + Q K^T — so the XU pipe and the tensor pipe took turns instead of overlapping: 26 % XU, 19 % tensor).
 // Window 0's zero look-back keys (reference quirk Q1) enter analytically: m starts at 0 and l at w.
 #include "tc_ptx.cuh"
 #include "../../include/progen_b200.h"
@@ -74,8 +78,11 @@ __device__ __forceinline__ int key_pos(const FwdDev& a, const Item& it, int kt) 
   return kt < it.nprev ? (it.win - 1) * a.w + kt * BKV : it.win * a.w + (kt - it.nprev) * BKV;
 }
 
-// POLY: every 4th exponential of a row is evaluated on the FMA pipe instead of the MUFU
-template <bool POLY>
+// POLY: every 4th exponential of a row is evaluated on the FMA pipe instead of the MUFU.
+// LOCK: the two softmax warps that share an SM sub-partition (one of each group) take turns in their exponential loops
+// (a shared-memory lock per sub-partition), so one group's XU-bound phase runs against the other group's loads / maximum /
+// stores instead of both halving each other's MUFU rate at the same time.
+template <bool POLY, bool LOCK>
 __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdDev a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -90,7 +97,9 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
   auto p_full = [&](int g) { return bars + 112 + 8 * g; };
   auto o_done = [&](int g) { return bars + 128 + 8 * g; };
   auto o_free = [&](int g) { return bars + 144 + 8 * g; };
-  const uint32_t tmem_slot = bars + 160;
+  auto s_read = [&](int g) { return bars + 160 + 8 * g; };
+  const uint32_t tmem_slot = bars + 176;
+  volatile int* xu_lock = reinterpret_cast<volatile int*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (bars - smem_base) + 192);   // [4], one per SMSP
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,7 +114,9 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
       mbar_init(p_full(g), 4);       // one arrival per softmax warp of the group
       mbar_init(o_done(g), 1);
       mbar_init(o_free(g), 4);
+      mbar_init(s_read(g), 4);
     }
+    for (int i = 0; i < 4; ++i) xu_lock[i] = 0;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
         constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, false, false);     // S[128 x 128] = Q (K-major) x K (K-major)
         constexpr uint32_t idesc_pv = make_idesc(BQ, DH, false, true);       // O[128 x 64] += P (TMEM) x V (MN-major)
         const int g = warp == 1 ? 0 : 1;
-        const uint32_t tS = tmem_base + g * BKV, tO = tmem_base + 256 + g * DH;
+        const uint32_t tS = tmem_base + g * BKV, tO = tmem_base + 256 + g * DH, tP = tmem_base + 384 + g * DH;
         int stage = 0;
         uint32_t kv_phase = 0, item = 0, pcount = 0;
         Item it;
@@ -163,27 +174,29 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
           const int n_g = it.nA + g, n_all = it.nA + 1;
           mbar_wait(q_full(qb), (item >> 1) & 1);
           mbar_wait(kv_full(stage), kv_phase);
+          if (pcount > 0) mbar_wait(s_read(g), (pcount - 1) & 1);              // the previous item's last S_g has been read
           issue_qk(qb, stage);
           for (int j = 0; j < n_all; ++j) {
             int nstage = stage + 1;
             uint32_t nphase = kv_phase;
             if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
             if (j < n_g) {
-              mbar_wait(p_full(g), pcount & 1);                              // P_g(j) is in TMEM (and S_g(j) has been read)
+              if (j + 1 < n_g) {
+                mbar_wait(kv_full(nstage), nphase);
+                mbar_wait(s_read(g), pcount & 1);                            // S_g(j) is in the group's registers: S_g is free
+                issue_qk(qb, nstage);                                        // runs under the group's exponentials of tile j
+              } else {
+                tcgen05_commit(q_empty(qb));                                 // every Q K^T of this group has been issued
+              }
+              mbar_wait(p_full(g), pcount & 1);                              // P_g(j) is in tensor memory
               ++pcount;
               if (j == 0 && item > 0) mbar_wait(o_free(g), (item - 1) & 1);    // previous item's O_g has been read out
               tcgen05_fence_after();
               const uint64_t vd = make_smem_desc<true>(sKV + stage * KV_BYTES + K_BYTES);
 #pragma unroll
               for (int k = 0; k < BKV / 16; ++k)
-                umma_bf16_ts(tO, tS + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_ts(tO, tP + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
               tcgen05_commit(o_done(g));
-              if (j + 1 < n_g) {
-                mbar_wait(kv_full(nstage), nphase);
-                issue_qk(qb, nstage);                                        // ordered behind P V (it overwrites P_g)
-              } else {
-                tcgen05_commit(q_empty(qb));                                 // every Q K^T of this group has been issued
-              }
               tcgen05_commit(kv_empty(stage));                               // my MMAs on K_j / V_j (the other issuer adds its own)
             } else {
               // a tile only the other group uses: wait until it has landed so the arrival lands in the right phase
@@ -206,6 +219,8 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
     const float sc = 0.125f * LOG2E;                                        // 1/sqrt(64) in log2 units
     const uint32_t s_addr = tmem_base + g * BKV + lane_addr;
     const uint32_t o_addr = tmem_base + 256 + g * DH + lane_addr;
+    const uint32_t p_addr = tmem_base + 384 + g * DH + lane_addr;
+    int* my_lock = const_cast<int*>(xu_lock) + q;
     uint32_t tcount = 0, item = 0;                                          // tiles processed by this group (barrier parity)
     Item it;
     for (int wi = blockIdx.x; decode_item(a, wi, it); wi += gridDim.x, ++item) {
@@ -224,6 +239,9 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < nch) tmem_ld32_wait(s[c]);                                // (names the registers: no use may move above it)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_read(g));                              // S_g is in registers: the next Q K^T may overwrite it
         // row maximum (chunks above the diagonal are skipped, the diagonal chunk is masked per element)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -245,6 +263,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
         }
         const float m_cand = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc);
         const bool need = m_cand - m_used > RESCALE_THRESHOLD;              // also true on the first tile (m_used = -inf)
+        bool pv_waited = false;
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? m_cand : m_used;
           const float corr = ex2f(m_used - m_new);                          // ex2(-inf) = 0 on the first tile
@@ -253,6 +272,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
           if (j > 0) {
             mbar_wait(o_done(g), (tcount - 1) & 1);                         // P V of the previous step has retired
             tcgen05_fence_after();
+            pv_waited = true;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {                                // 32 columns at a time: S stays live in registers
               uint32_t o[32];
@@ -264,12 +284,16 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
             }
           }
         }
-        // p = exp2(s c - m), packed to bf16 pairs and written over S[0, 64) chunk by chunk
+        // p = exp2(s c - m), packed to bf16 pairs; written to P_g once the previous P V (which reads P_g) has retired
         const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_used, -m_used);
         float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
+        uint32_t pk[4][16];
+        if (LOCK) {
+          if (lane == 0) while (atomicExch(my_lock, 1) != 0) __nanosleep(32);
+          __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
           if (c < nch) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -281,15 +305,24 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
               x1.y = POLY ? ex2_poly(x1.y) : ex2f(x1.y);
               rs0 = fadd2(rs0, x0);
               rs1 = fadd2(rs1, x1);
-              pk[i / 2] = pack_bf16x2(x0.x, x0.y);
-              pk[i / 2 + 1] = pack_bf16x2(x1.x, x1.y);
+              pk[c][i / 2] = pack_bf16x2(x0.x, x0.y);
+              pk[c][i / 2 + 1] = pack_bf16x2(x1.x, x1.y);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            for (int i = 0; i < 16; ++i) pk[c][i] = 0u;
           }
-          tmem_st<16>(s_addr + c * 16, pk);
         }
+        if (LOCK) {
+          __syncwarp();
+          if (lane == 0) atomicExch(my_lock, 0);
+        }
+        if (j > 0 && !pv_waited) {
+          mbar_wait(o_done(g), (tcount - 1) & 1);                           // P V of the previous step no longer reads P_g
+          tcgen05_fence_after();
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st<16>(p_addr + c * 16, pk[c]);
         l_run += (rs0.x + rs0.y) + (rs1.x + rs1.y);
         tmem_st_wait();
         tcgen05_fence_before();                                             // my TMEM reads / writes precede the MMAs that follow
@@ -348,15 +381,20 @@ int attn_fwd_ts_launch(const void* qkv, void* out, float* lse, int B, int seq_le
   if (rc) return rc;
   static bool once = false;
   if (!once) {
-    PG_CUDA(cudaFuncSetAttribute(attn_fwd_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    PG_CUDA(cudaFuncSetAttribute(attn_fwd_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PG_CUDA(cudaFuncSetAttribute(attn_fwd_ts_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PG_CUDA(cudaFuncSetAttribute(attn_fwd_ts_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PG_CUDA(cudaFuncSetAttribute(attn_fwd_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PG_CUDA(cudaFuncSetAttribute(attn_fwd_ts_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     once = true;
   }
   FwdDev a{B, seq_len, window, heads, (bf16*)out, lse};
   const long long items = (long long)B * heads * (seq_len / (2 * BQ));
   const int grid = (int)(items < pg_num_sms() ? items : pg_num_sms());
-  if (mode >= 2) attn_fwd_ts_kernel<true><<<grid, 384, SMEM_BYTES, stream>>>(tm, a);
-  else attn_fwd_ts_kernel<false><<<grid, 384, SMEM_BYTES, stream>>>(tm, a);
+  // mode: 1 MUFU only, 2 + FMA-pipe exp2 share, 3 = 1 + XU lock, 4 = 2 + XU lock
+  if (mode == 4) attn_fwd_ts_kernel<true, true><<<grid, 384, SMEM_BYTES, stream>>>(tm, a);
+  else if (mode == 3) attn_fwd_ts_kernel<false, true><<<grid, 384, SMEM_BYTES, stream>>>(tm, a);
+  else if (mode == 2) attn_fwd_ts_kernel<true, false><<<grid, 384, SMEM_BYTES, stream>>>(tm, a);
+  else attn_fwd_ts_kernel<false, false><<<grid, 384, SMEM_BYTES, stream>>>(tm, a);
   PG_LAUNCH_CHECK();
   return PROGEN_OK;
 }

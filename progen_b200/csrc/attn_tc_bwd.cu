@@ -14,6 +14,9 @@
 #include "tc_ptx.cuh"
 #include "../../include/progen_b200.h"
 
+int attn_bwd_ts_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                       const float* rot_sin, const float* rot_cos, int B, int seq_len, int window, int heads, cudaStream_t s);
+
 namespace {
 
 using namespace tc;
@@ -491,6 +494,9 @@ int progen_local_attn_bwd_tc(const void* qkv, const void* out, const void* dout,
                              const float* rot_sin, const float* rot_cos, int B, int seq_len, int window, int heads, int dim_head,
                              void* stream) {
   PG_CHECK_ARG(B > 0 && heads > 0 && dim_head == DH && window % 128 == 0 && seq_len % window == 0);
+  // round-2 kernels (element-wise results in tensor memory, alternating groups; attn_bwd_ts.cu)
+  const int rc_ts = attn_bwd_ts_launch(qkv, out, dout, lse, dqkv, delta, rot_sin, rot_cos, B, seq_len, window, heads, (cudaStream_t)stream);
+  if (rc_ts <= 0) return rc_ts;
   const long long T = (long long)B * seq_len;
   const int I = heads * DH;
   CUtensorMap tq_row, tq_col, tdo_row, tdo_col;

@@ -8,7 +8,7 @@ mkdir -p "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3
        --expt-relaxed-constexpr -DCUDA_VERSION_STR="\"12.9\"" -I"$HERE" -I"$HERE/../../include")
-SRCS=(api gemm_tc gemm_tc2 gemm_simt elementwise ln_stream attn_simt attn_mma attn_tc attn_tc_pair attn_fwd_ts attn_tc_bwd optim decode)
+SRCS=(api gemm_tc gemm_tc2 gemm_simt elementwise ln_stream attn_simt attn_mma attn_tc attn_tc_pair attn_fwd_ts attn_tc_bwd attn_bwd_ts optim decode decode_persist)
 pids=()
 for s in "${SRCS[@]}"; do
   [ -f "$HERE/$s.cu" ] || continue

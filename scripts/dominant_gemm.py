@@ -1,8 +1,8 @@
-"""Launch only bench.py's dominant kernel (KERNEL=wgrad: FF proj_in weight gradient, default; KERNEL=glu: FF proj_in
-forward GEMM with the GLU epilogue; config-2 shapes) a few times.
+"""Launch only the kernels bench.py's `roofline` object times (bench.time_step_kernels: attention forward / backward, FF
+proj_in weight gradient, FF proj_in + GLU, FF proj_out dgrad + GLU backward; config-2 shapes) a few times.
 
-Meant to sit under `ncu --set full -k regex:gemm_tc -c 1 --launch-skip N` so the capture holds exactly the kernel whose
-roofline bench.py reports; prints the CUDA-event timing when run bare."""
+Meant to sit under `ncu --set full -k regex:<kernel> -c N --profile-from-start off` so the capture holds exactly the
+kernels whose roofline bench.py reports; prints the CUDA-event timings when run bare."""
 import json
 import os
 import sys
@@ -28,7 +28,7 @@ def main():
     tr.step_resident(global_batch=B)           # populates the saved activations the GEMM reads
     torch.cuda.synchronize()
     torch.cuda.profiler.start()                # ncu --profile-from-start off: only the launches below are visible
-    res = bench.time_dominant_gemm(eng, iters=int(os.environ.get('ITERS', '5')), which=os.environ.get('KERNEL', 'wgrad'))
+    res = bench.time_step_kernels(eng, kw, iters=int(os.environ.get('ITERS', '5')))
     torch.cuda.profiler.stop()
     print('DOMINANT ' + json.dumps(res))
 

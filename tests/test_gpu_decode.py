@@ -70,3 +70,110 @@ def test_bf16_weight_decode_runs_and_mostly_agrees():
     a, _, _ = Decoder(cfg, params).sample(g['prime'], top_k=25, add_bos=True, greedy=True)
     b, _, _ = Decoder(cfg, params, weights_dtype=torch.bfloat16).sample(g['prime'], top_k=25, add_bos=True, greedy=True)
     assert a.shape == b.shape and (a[:len(g['prime']) + 2] == b[:len(g['prime']) + 2]).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: the whole generation in ONE persistent kernel (csrc/decode_persist.cu), single stream and batched
+
+@pytest.mark.parametrize('name', TINY)
+@pytest.mark.parametrize('add_bos', [False, True])
+def test_persistent_greedy_ids_match_reference_sampler(name, add_bos):
+    from progen_b200.decode import BatchDecoder
+    cfg, params, data, g = load_case(name)
+    dec = BatchDecoder(cfg, params, batch=1, keep_logits=True)
+    ids, gen, secs = dec.sample(g['prime'], top_k=25, add_bos=add_bos, greedy=True)
+    np.testing.assert_array_equal(ids, g[f'sample_bos{int(add_bos)}'])
+    assert gen > 0 and secs > 0
+
+
+def test_persistent_logits_match_oracle_forward():
+    from progen_b200.decode import BatchDecoder
+    from oracle import progen_ref as O
+    cfg, params, data, g = load_case('tiny_glu_sgu')
+    dec = BatchDecoder(cfg, params, batch=1, keep_logits=True)
+    dec.sample(g['prime'], top_k=25, add_bos=True, greedy=True)
+    seq = dec.seq.cpu().numpy().astype(np.int64)[0]
+    ref = O.forward(params, np.clip(seq, 0, 255), cfg)
+    got = dec.logits_all.cpu().numpy()[0]
+    n = cfg['seq_len']
+    assert np.abs(got[:n - 1] - ref[:n - 1]).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize('B', [3, 8, 33])
+def test_batched_decode_equals_single_stream(B):
+    """B primes of different lengths decoded in lock step == each prime decoded alone (greedy, bit-equal ids)"""
+    from progen_b200.decode import BatchDecoder
+    cfg, params, data, g = load_case('tiny_glu_sgu')
+    rng = np.random.default_rng(B)
+    primes = [rng.integers(1, 256, int(rng.integers(1, 9))).astype(np.int64) for _ in range(B)]
+    primes[0] = np.asarray(g['prime']).astype(np.int64)
+    batch, gen, secs = BatchDecoder(cfg, params, batch=B).sample(primes, top_k=25, add_bos=True, greedy=True)
+    single = BatchDecoder(cfg, params, batch=1)
+    for b in range(B):
+        one, _, _ = single.sample(primes[b], top_k=25, add_bos=True, greedy=True)
+        np.testing.assert_array_equal(batch[b], one)
+    np.testing.assert_array_equal(batch[0], g['sample_bos1'])
+
+
+def test_persistent_decode_cfg1_size_matches_graph_decoder():
+    """BASELINE config-5 shape on the config-1 model: persistent kernel == round-1 per-step decoder (which is pinned to the
+    full re-forward sampler), fp32 and bit-equal"""
+    from progen_b200.decode import Decoder, BatchDecoder
+    from progen_b200.data import encode_tokens
+    cfg, params, data, g = load_case('cfg1')
+    prime = np.array(encode_tokens('[Tax=Mammalia] #'), dtype=np.uint16)
+    a, _, _ = Decoder(cfg, params).sample(prime, top_k=25, add_bos=True, greedy=True)
+    b, gen, secs = BatchDecoder(cfg, params, batch=1).sample(prime, top_k=25, add_bos=True, greedy=True)
+    np.testing.assert_array_equal(a, b)
+    print(f'persistent decode: {gen} tokens in {secs * 1e3:.1f} ms = {gen / secs:.0f} tokens/s')
+
+
+def test_gumbel_topk_sampler_distribution_chi_square():
+    """Distribution-level parity of the stochastic sampler: the device sampler draws
+    argmax(filtered logits + gumbel) with the reference's quirky top-k filter (utils.py:97-100,121-125: keeps the k-1
+    logits above the k-th, sets the rest to 0.0 and removes their noise).  For the FIRST sampled position of many
+    independently seeded runs the empirical distribution must match the probabilities that filter implies:
+    softmax over {kept logits} U {one atom of value 0.0 standing for all filtered entries (they tie at 0, argmax takes
+    the first)}.  Chi-square goodness of fit at the 0.1 % level."""
+    from scipy import stats
+    from progen_b200.decode import BatchDecoder
+    from oracle import progen_ref as O
+    cfg, params, data, g = load_case('tiny_all_glu')
+    prime = np.asarray(g['prime']).astype(np.int64)
+    B, K, runs = 64, 25, 12
+    dec = BatchDecoder(cfg, params, batch=B)
+    P_ = len(prime)
+    counts = np.zeros(cfg['num_tokens'], np.int64)
+    for r_ in range(runs):
+        ids, _, _ = dec.sample([prime] * B, top_k=K, add_bos=False, greedy=False, seed=1000 + r_)
+        # without add_bos position P_ starts at 0, so seq[P_] IS the sampled id of the first draw
+        first = dec.seq.cpu().numpy()[:, P_]
+        counts += np.bincount(first, minlength=cfg['num_tokens'])
+    seq = np.pad(prime, (0, cfg['seq_len'] - P_))
+    logits = O.forward(params, seq, cfg)[P_ - 1].astype(np.float64)
+    kth = np.sort(logits)[-K]
+    keep = logits > kth
+    z = np.where(keep, logits, 0.0)
+    first_filtered = int(np.argmin(keep))                 # all filtered entries tie at 0.0 (no noise): argmax returns the first
+    atoms = np.zeros_like(z)
+    atoms[keep] = np.exp(z[keep])
+    atoms[first_filtered] = 1.0                            # exp(0): Gumbel-max against a noiseless 0 is NOT a softmax atom ...
+    # ... a noiseless entry wins iff every kept (logit + gumbel) < 0: P = prod_i exp(-exp(l_i)) = exp(-sum_i exp(l_i))
+    S = np.exp(logits[keep]).sum()
+    p0 = np.exp(-S)
+    probs = np.zeros_like(z)
+    probs[keep] = (1.0 - p0) * np.exp(logits[keep]) / S    # given some kept entry is > 0 ... (exactly: max-stability of Gumbel)
+    probs[first_filtered] = p0
+    # exact law: M = max_i(l_i + G_i) ~ Gumbel(log S); argmax independent of M; P(M < 0) = exp(-S)
+    n_draws = counts.sum()
+    assert n_draws == B * runs
+    assert counts[~keep & (np.arange(len(keep)) != first_filtered)].sum() == 0
+    exp_counts = probs * n_draws
+    big = exp_counts >= 5
+    obs = np.append(counts[big], counts[~big].sum())
+    exp_ = np.append(exp_counts[big], exp_counts[~big].sum())
+    if exp_[-1] == 0:
+        obs, exp_ = obs[:-1], exp_[:-1]
+    chi2 = ((obs - exp_) ** 2 / exp_).sum()
+    pval = 1.0 - stats.chi2.cdf(chi2, len(obs) - 1)
+    assert pval > 1e-3, (chi2, len(obs), pval)
