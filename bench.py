@@ -34,6 +34,11 @@ CONFIGS = {
     'cfg4': dict(kwargs=dict(num_tokens=256, dim=1536, seq_len=4096, depth=36, heads=8, dim_head=64, window_size=256,
                              global_mlp_depth=2, ff_glu=True), batch=4,
                  name='ProGen dim=1536 depth=36 seq_len=4096 window=256 ff_glu bf16 - training step (BASELINE configs[3])'),
+    # BASELINE.json configs[4]: sample.py decode, seq_len 1024, prime '[Tax=Mammalia] #', on the configs[1] model
+    'cfg5': dict(kwargs=dict(num_tokens=256, dim=512, seq_len=1024, depth=12, heads=8, dim_head=64, window_size=256,
+                             global_mlp_depth=2, ff_glu=True), batch=1, decode=True,
+                 name="sample.py autoregressive decode seq_len=1024, prime='[Tax=Mammalia] #', top_k=25, add_bos - ProGen dim=512 "
+                      "depth=12 heads=8 window=256 gmlp=2, bf16 weights, KV-cached persistent kernel (BASELINE configs[4])"),
     'tiny': dict(kwargs=dict(num_tokens=256, dim=128, seq_len=128, depth=2, heads=2, dim_head=64, window_size=64,
                              global_mlp_depth=1, ff_glu=True), batch=4, name='tiny smoke configuration (not a bench line)'),
 }
@@ -150,11 +155,149 @@ def cpu_port_tokens_per_sec(kw, steps, warmup, rows=1, seed=123, budget_s=60.0):
     return rows * n / sec, sec, rows, len(times)
 
 
+def decode_bytes_per_token(kw, wbytes):
+    """algorithmic HBM bytes one decoded position must move: every weight once (`wbytes` per element; the embedding row and
+    the SGU spatial row are negligible), the visible K / V rows of every layer (fp32 cache, on average w + w/2 keys), the
+    gate history of the gMLP layers (on average n/2 rows)"""
+    d, n, w, L = kw['dim'], kw['seq_len'], kw['window_size'], kw['depth']
+    I = kw['heads'] * kw['dim_head']
+    hid = 4 * d
+    nsgu = min(L, kw['global_mlp_depth'])
+    per_glu = d * 3 * I + I * d + d * 2 * hid + hid * d
+    per_sgu = d * 3 * I + I * d + d * hid + (hid // 2) ** 2 + (hid // 2) * d
+    weights = ((L - nsgu) * per_glu + nsgu * per_sgu + d * kw['num_tokens']) * wbytes
+    kv = L * 2 * (w + w / 2) * I * 4
+    hist = nsgu * (n / 2) * (hid // 2) * 4
+    return weights, kv + hist
+
+
+def cpu_decode_tokens_per_sec(kw, prime, tokens=4):
+    """the reference's sampler on the host: one FULL forward of the padded sequence per generated token (utils.py:115-117),
+    oracle NumPy/torch port, fp32, bounded to a few tokens"""
+    from oracle import progen_ref as O
+    from oracle import progen_torch as T
+    torch.set_num_threads(cpu_threads())
+    cfg = O.make_config(**kw)
+    prm = T.to_torch(O.init_params(cfg, 0), torch.float32)
+    n = cfg['seq_len']
+    seq = torch.zeros(1, n, dtype=torch.int64)
+    seq[0, 1:1 + len(prime)] = torch.as_tensor(np.asarray(prime).astype(np.int64))
+    times = []
+    with torch.no_grad():
+        for i in range(tokens + 1):
+            t0 = time.perf_counter()
+            logits = T.forward(prm, seq, cfg)[0, len(prime) + i]
+            seq[0, len(prime) + 1 + i] = int(torch.argmax(logits))
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+    return 1.0 / (sum(times) / len(times)), len(times)
+
+
+def run_decode_bench(args, cfgd):
+    """BASELINE configs[4]: tokens/s of the KV-cached sampler.  A "step" = one whole generation (seq_len - prime tokens) of
+    one sequence per GPU; `value` = generated tokens / device time with the prime already on the device; `e2e` = the
+    public call with the prime on the host and the ids read back.  Beside it: B = 64 primes decoded in lock step."""
+    import torch.distributed as dist
+    from progen_b200 import ProGen, lib as L
+    from progen_b200.decode import BatchDecoder
+    from progen_b200.data import encode_tokens
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    L.require_device()
+    kw = cfgd['kwargs']
+    n = kw['seq_len']
+    model = ProGen(**kw)
+    params = model.init(1234)
+    prime = np.array(encode_tokens('[Tax=Mammalia] #'), dtype=np.int64)
+    wdt = torch.float32 if args.fp32 else torch.bfloat16
+    dec = BatchDecoder(model.config, params, batch=1, weights_dtype=wdt)
+    c0 = L.load().progen_launch_count()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        dec.sample(prime, top_k=25, add_bos=True, greedy=False, seed=rank)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    dev_s, gen_tokens = 0.0, 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ids, gen, secs = dec.sample(prime, top_k=25, add_bos=True, greedy=False, seed=100 + i)
+        dev_s += secs
+        gen_tokens += gen
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    launches = L.load().progen_launch_count() - c0
+    t = torch.tensor([dev_s, wall_s], device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, wall_s = float(t[0]), float(t[1])
+    tps = gen_tokens * world / dev_s
+    tps_e2e = gen_tokens * world / wall_s
+    # batched: 64 primes in lock step
+    Bb = 64
+    decb = BatchDecoder(model.config, params, batch=Bb, weights_dtype=wdt)
+    decb.sample([prime] * Bb, top_k=25, add_bos=True, greedy=False, seed=7)
+    _, genb, secb = decb.sample([prime] * Bb, top_k=25, add_bos=True, greedy=False, seed=8)
+    if rank == 0:
+        peaks = measured_peaks()
+        wb, rest = decode_bytes_per_token(kw, 4 if args.fp32 else 2)
+        per_tok_s = dev_s / gen_tokens
+        achieved = (wb + rest) / per_tok_s / 1e9
+        per_step_b = secb / (genb / Bb)
+        achieved_b = (wb + Bb * rest) / per_step_b / 1e9
+        roofline = dict(bound='hbm', achieved=achieved, peak=peaks['hbm'], unit='GB/s', frac=achieved / peaks['hbm'], traffic=None,
+                        kernel='decode_persistent_kernel<1, bf16> (one cooperative kernel for the whole generation)',
+                        algorithmic_bytes_per_token=wb + rest, us_per_token=per_tok_s * 1e6, peak_source=peaks['source'],
+                        batched=dict(batch=Bb, tokens_per_sec=genb / secb, us_per_step=per_step_b * 1e6, achieved=achieved_b,
+                                     frac=achieved_b / peaks['hbm'], algorithmic_bytes_per_step=wb + Bb * rest))
+        line = dict(metric='decode_tokens_per_sec', value=tps, unit='tokens/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=dev_s / args.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f32' if args.fp32 else 'bf16', data='synthetic',
+                    config=dict(workload=cfgd['name'], global_batch=world, seq_len=n, parallelism=f'replicas x{world}',
+                                l2='weights (103 MB bf16) fit the 126 MB L2; every position still streams them from L2/HBM once',
+                                step='one generation of %d tokens' % (gen_tokens // args.steps)),
+                    e2e=dict(value=tps_e2e, unit='tokens/s', h2d_bytes_per_step=int(n * 4 + 4), d2h_bytes_per_step=int(n * 4),
+                             ms_per_step=wall_s / args.steps * 1e3),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline)
+        if not args.no_cpu_baseline and world == 1:
+            v, timed = cpu_decode_tokens_per_sec(kw, prime)
+            line['cpu_baseline'] = dict(value=v, unit='tokens/s', cores=cpu_threads(), kind='port',
+                                        sample=f'{timed} generated tokens, one full {n}-token forward each (reference sampler), fp32')
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference_arm(args, cfgd):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     kw = cfgd['kwargs']
+    if cfgd.get('decode'):
+        from progen_b200.data import encode_tokens
+        prime = np.array(encode_tokens('[Tax=Mammalia] #'), dtype=np.int64)
+        v, timed = cpu_decode_tokens_per_sec(kw, prime, tokens=max(2, min(args.steps, 8)))
+        line = dict(impl='reference', metric='decode_tokens_per_sec', value=v, unit='tokens/s', n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=1e3 / v, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                    data='synthetic', config=dict(workload=cfgd['name']),
+                    cpu_baseline=dict(value=v, unit='tokens/s', cores=cpu_threads(), kind='port',
+                                      sample=f'{timed} generated tokens, one full forward each'),
+                    e2e=dict(value=v, unit='tokens/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    note='oracle torch port of the reference sampler (full re-forward per token) on the host cores')
+        print(json.dumps(line), flush=True)
+        return
     cores = cpu_threads()
     # bounded sample: one sequence per step; the loop stops once ~60 s of timed work has accumulated (a step takes
     # 0.6 s on an idle box and up to 40 s on a loaded one), so the whole arm ends within a few minutes either way
@@ -260,6 +403,9 @@ def main():
     kw = cfgd['kwargs']
     if args.impl == 'reference':
         run_reference_arm(args, cfgd)
+        return
+    if cfgd.get('decode'):
+        run_decode_bench(args, cfgd)
         return
 
     import torch.distributed as dist

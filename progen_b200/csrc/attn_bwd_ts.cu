@@ -141,23 +141,29 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_ts_kernel(const __grid_co
     setmaxnreg_dec<72>();
     if (warp == 0) {
       // ------------------------------------------------------------------------------------------ TMA producer
-      if (lane == 0) {
+      {                                                       // whole warp, one elected lane issues (uniform operands)
         uint32_t x = 0, item = 0;
         KItem it;
         for (int wi = blockIdx.x; decode_kitem(a, wi, it); wi += gridDim.x, ++item) {
           const int row0 = it.b * a.n, kvb = item & 1;
           mbar_wait(kv_empty(kvb), ((item >> 1) & 1) ^ 1);
-          mbar_expect_tx(kv_full(kvb), 2 * ROW_TILE_BYTES);
-          tma_load_2d(sKV + (2 * kvb) * ROW_TILE_BYTES, &tmap_qkv_row, kv_full(kvb), I + it.hh * DH, row0 + it.k0);
-          tma_load_2d(sKV + (2 * kvb + 1) * ROW_TILE_BYTES, &tmap_qkv_row, kv_full(kvb), 2 * I + it.hh * DH, row0 + it.k0);
+          if (elect_one()) {
+            mbar_expect_tx(kv_full(kvb), 2 * ROW_TILE_BYTES);
+            tma_load_2d(sKV + (2 * kvb) * ROW_TILE_BYTES, &tmap_qkv_row, kv_full(kvb), I + it.hh * DH, row0 + it.k0);
+            tma_load_2d(sKV + (2 * kvb + 1) * ROW_TILE_BYTES, &tmap_qkv_row, kv_full(kvb), 2 * I + it.hh * DH, row0 + it.k0);
+          }
+          __syncwarp();
           for (int t = 0; t < it.nT; ++t, ++x) {
             const int st = x % NS;
             mbar_wait(qs_empty(st), ((x / NS) & 1) ^ 1);
             const uint32_t dst = sQS + st * STAGE_BYTES;
             const int qp = row0 + q_pos(it, t);
-            mbar_expect_tx(qs_full(st), STAGE_BYTES);
-            tma_load_2d(dst, &tmap_qkv_col, qs_full(st), it.hh * DH, qp);
-            tma_load_2d(dst + COL_TILE_BYTES, &tmap_do_col, qs_full(st), it.hh * DH, qp);
+            if (elect_one()) {
+              mbar_expect_tx(qs_full(st), STAGE_BYTES);
+              tma_load_2d(dst, &tmap_qkv_col, qs_full(st), it.hh * DH, qp);
+              tma_load_2d(dst + COL_TILE_BYTES, &tmap_do_col, qs_full(st), it.hh * DH, qp);
+            }
+            __syncwarp();
           }
         }
       }
@@ -184,7 +190,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_ts_kernel(const __grid_co
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------------------------------------ MMA issuer
-      if (lane == 0) {
+      // (whole warp: descriptors stay in uniform registers — see tc::elect_one; one elected lane issues tcgen05)
+      {
         constexpr uint32_t idesc_s = make_idesc(RB, CT, false, false);      // S^T / dP^T [128 keys x 64 queries], K = dh
         constexpr uint32_t idesc_a = make_idesc(RB, DH, false, true);       // dV / dK [128 keys x 64 dh], K = queries, B MN-major
         struct Cur { int wi; uint32_t item; int t; KItem it; bool valid; };
@@ -205,12 +212,15 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_ts_kernel(const __grid_co
           const uint64_t vd = make_smem_desc<false>(sKV + (2 * kvb + 1) * ROW_TILE_BYTES);
           const uint64_t qd = make_smem_desc<false>(sQS + st * STAGE_BYTES), dod = make_smem_desc<false>(sQS + st * STAGE_BYTES + COL_TILE_BYTES);
           const uint32_t tm = tmem_base + buf * 128;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16(tm, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tm, kd + 2 * k, qd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16(tm + 64, vd + 2 * k, dod + 2 * k, idesc_s, k > 0);
-          tcgen05_commit(s_full(buf));
-          if (ahead.t == ahead.it.nT - 1) tcgen05_commit(kv_empty(kvb));     // the item's K / V tiles have had their last reader
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tm + 64, vd + 2 * k, dod + 2 * k, idesc_s, k > 0);
+            tcgen05_commit(s_full(buf));
+            if (ahead.t == ahead.it.nT - 1) tcgen05_commit(kv_empty(kvb));   // the item's K / V tiles have had their last reader
+          }
+          __syncwarp();
           advance(ahead);
           ++xa;
         };
@@ -224,14 +234,17 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_ts_kernel(const __grid_co
           const uint64_t domn = make_smem_desc<true>(sQS + st * STAGE_BYTES + COL_TILE_BYTES);
           const uint32_t tm = tmem_base + buf * 128;
           const uint32_t acc = cur.t > 0 ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < CT / 16; ++k)                                  // dV += P^T dO_t
-            umma_bf16_ts(tmem_base + 448, tm + 8 * k, domn + (uint64_t)(k * (2048 >> 4)), idesc_a, (acc || k > 0) ? 1u : 0u);
+            for (int k = 0; k < CT / 16; ++k)                                // dV += P^T dO_t
+              umma_bf16_ts(tmem_base + 448, tm + 8 * k, domn + (uint64_t)(k * (2048 >> 4)), idesc_a, (acc || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < CT / 16; ++k)                                  // dK += dS^T Q_t
-            umma_bf16_ts(tmem_base + 384, tm + 64 + 8 * k, qmn + (uint64_t)(k * (2048 >> 4)), idesc_a, (acc || k > 0) ? 1u : 0u);
-          tcgen05_commit(qs_empty(st));
-          if (cur.t == cur.it.nT - 1) tcgen05_commit(acc_full);
+            for (int k = 0; k < CT / 16; ++k)                                // dK += dS^T Q_t
+              umma_bf16_ts(tmem_base + 384, tm + 64 + 8 * k, qmn + (uint64_t)(k * (2048 >> 4)), idesc_a, (acc || k > 0) ? 1u : 0u);
+            tcgen05_commit(qs_empty(st));
+            if (cur.t == cur.it.nT - 1) tcgen05_commit(acc_full);
+          }
+          __syncwarp();
           advance(cur);
           issue_ahead();                                                     // step x+3 into the buffer step x has just released
         }
@@ -390,28 +403,34 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_ts_kernel(const __grid_con
   if (warp < 4) {
     setmaxnreg_dec<72>();
     if (warp == 0) {
-      if (lane == 0) {
+      {                                                       // whole warp, one elected lane issues (uniform operands)
         uint32_t x = 0, item = 0;
         QItem it;
         for (int wi = blockIdx.x; decode_qitem(a, wi, it); wi += gridDim.x, ++item) {
           const int row0 = it.b * a.n, qb = item & 1;
           mbar_wait(qd_empty(qb), ((item >> 1) & 1) ^ 1);
-          mbar_expect_tx(qd_full(qb), 2 * ROW_TILE_BYTES);
-          tma_load_2d(sQD + (2 * qb) * ROW_TILE_BYTES, &tmap_qkv_row, qd_full(qb), it.hh * DH, row0 + it.q0);
-          tma_load_2d(sQD + (2 * qb + 1) * ROW_TILE_BYTES, &tmap_do_row, qd_full(qb), it.hh * DH, row0 + it.q0);
+          if (elect_one()) {
+            mbar_expect_tx(qd_full(qb), 2 * ROW_TILE_BYTES);
+            tma_load_2d(sQD + (2 * qb) * ROW_TILE_BYTES, &tmap_qkv_row, qd_full(qb), it.hh * DH, row0 + it.q0);
+            tma_load_2d(sQD + (2 * qb + 1) * ROW_TILE_BYTES, &tmap_do_row, qd_full(qb), it.hh * DH, row0 + it.q0);
+          }
+          __syncwarp();
           for (int j = 0; j < it.nT; ++j, ++x) {
             const int st = x % NS;
             mbar_wait(kv_empty(st), ((x / NS) & 1) ^ 1);
             const uint32_t dst = sKV + st * STAGE_BYTES;
             const int kp = row0 + key_pos(it, j);
-            mbar_expect_tx(kv_full(st), STAGE_BYTES);
-            tma_load_2d(dst, &tmap_qkv_col, kv_full(st), I + it.hh * DH, kp);
-            tma_load_2d(dst + COL_TILE_BYTES, &tmap_qkv_col, kv_full(st), 2 * I + it.hh * DH, kp);
+            if (elect_one()) {
+              mbar_expect_tx(kv_full(st), STAGE_BYTES);
+              tma_load_2d(dst, &tmap_qkv_col, kv_full(st), I + it.hh * DH, kp);
+              tma_load_2d(dst + COL_TILE_BYTES, &tmap_qkv_col, kv_full(st), 2 * I + it.hh * DH, kp);
+            }
+            __syncwarp();
           }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {                                                       // whole warp, one elected lane issues (uniform operands)
         constexpr uint32_t idesc_s = make_idesc(RB, CT, false, false);      // S / dP [128 q x 64 keys], K = dh
         constexpr uint32_t idesc_a = make_idesc(RB, DH, false, true);       // dQ [128 q x 64 dh] += dS (TMEM, K = keys) x K_j (MN-major)
         struct Cur { int wi; uint32_t item; int t; QItem it; bool valid; };
@@ -432,12 +451,15 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_ts_kernel(const __grid_con
           const uint64_t dod = make_smem_desc<false>(sQD + (2 * qb + 1) * ROW_TILE_BYTES);
           const uint64_t kd = make_smem_desc<false>(sKV + st * STAGE_BYTES), vd = make_smem_desc<false>(sKV + st * STAGE_BYTES + COL_TILE_BYTES);
           const uint32_t tm = tmem_base + buf * 128;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16(tm, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tm, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16(tm + 64, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
-          tcgen05_commit(s_full(buf));
-          if (ahead.t == ahead.it.nT - 1) tcgen05_commit(qd_empty(qb));      // the item's Q / dO tiles have had their last reader
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tm + 64, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
+            tcgen05_commit(s_full(buf));
+            if (ahead.t == ahead.it.nT - 1) tcgen05_commit(qd_empty(qb));    // the item's Q / dO tiles have had their last reader
+          }
+          __syncwarp();
           advance(ahead);
           ++xa;
         };
@@ -449,11 +471,14 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_ts_kernel(const __grid_con
           tcgen05_fence_after();
           const uint64_t kmn = make_smem_desc<true>(sKV + st * STAGE_BYTES);
           const uint32_t tm = tmem_base + buf * 128;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < CT / 16; ++k)                                  // dQ += dS K_j
-            umma_bf16_ts(tmem_base + 384, tm + 64 + 8 * k, kmn + (uint64_t)(k * (2048 >> 4)), idesc_a, (cur.t > 0 || k > 0) ? 1u : 0u);
-          tcgen05_commit(kv_empty(st));
-          if (cur.t == cur.it.nT - 1) tcgen05_commit(acc_full);
+            for (int k = 0; k < CT / 16; ++k)                                // dQ += dS K_j
+              umma_bf16_ts(tmem_base + 384, tm + 64 + 8 * k, kmn + (uint64_t)(k * (2048 >> 4)), idesc_a, (cur.t > 0 || k > 0) ? 1u : 0u);
+            tcgen05_commit(kv_empty(st));
+            if (cur.t == cur.it.nT - 1) tcgen05_commit(acc_full);
+          }
+          __syncwarp();
           advance(cur);
           issue_ahead();
         }

@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
     setmaxnreg_dec<64>();
     if (warp == 0) {
       // ============================================================================ TMA producer
-      if (lane == 0) {
+      // (the whole warp runs the loop so that addresses / coordinates are warp-uniform; one elected lane issues)
+      {
         int stage = 0;
         uint32_t kv_phase = 0, item = 0;
         Item it;
@@ -137,23 +138,30 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
           const int row0 = it.b * a.n;
           const int qb = item & 1;
           mbar_wait(q_empty(qb), ((item >> 1) & 1) ^ 1);
-          mbar_expect_tx(q_full(qb), 2 * Q_BYTES);
-          tma_load_2d(sQ + (2 * qb) * Q_BYTES, &tmap_qkv, q_full(qb), it.hh * DH, row0 + it.q0);
-          tma_load_2d(sQ + (2 * qb + 1) * Q_BYTES, &tmap_qkv, q_full(qb), it.hh * DH, row0 + it.q0 + BQ);
+          if (elect_one()) {
+            mbar_expect_tx(q_full(qb), 2 * Q_BYTES);
+            tma_load_2d(sQ + (2 * qb) * Q_BYTES, &tmap_qkv, q_full(qb), it.hh * DH, row0 + it.q0);
+            tma_load_2d(sQ + (2 * qb + 1) * Q_BYTES, &tmap_qkv, q_full(qb), it.hh * DH, row0 + it.q0 + BQ);
+          }
+          __syncwarp();
           for (int kt = 0; kt <= it.nA; ++kt) {
             mbar_wait(kv_empty(stage), kv_phase ^ 1);
             const uint32_t dst = sKV + stage * KV_BYTES;
             const int kp = row0 + key_pos(a, it, kt);
-            mbar_expect_tx(kv_full(stage), KV_BYTES);
-            tma_load_2d(dst, &tmap_qkv, kv_full(stage), I + it.hh * DH, kp);
-            tma_load_2d(dst + K_BYTES, &tmap_qkv, kv_full(stage), 2 * I + it.hh * DH, kp);
+            if (elect_one()) {
+              mbar_expect_tx(kv_full(stage), KV_BYTES);
+              tma_load_2d(dst, &tmap_qkv, kv_full(stage), I + it.hh * DH, kp);
+              tma_load_2d(dst + K_BYTES, &tmap_qkv, kv_full(stage), 2 * I + it.hh * DH, kp);
+            }
+            __syncwarp();
             if (++stage == KV_STAGES) { stage = 0; kv_phase ^= 1; }
           }
         }
       }
     } else if (warp == 1 || warp == 3) {
       // ============================================================================ MMA issuer of group g
-      if (lane == 0) {
+      // (whole warp: descriptors stay in uniform registers — see tc::elect_one; one elected lane issues tcgen05)
+      {
         constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, false, false);     // S[128 x 128] = Q (K-major) x K (K-major)
         constexpr uint32_t idesc_pv = make_idesc(BQ, DH, false, true);       // O[128 x 64] += P (TMEM) x V (MN-major)
         const int g = warp == 1 ? 0 : 1;
@@ -165,9 +173,12 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
           tcgen05_fence_after();
           const uint64_t ad = make_smem_desc<false>(sQ + (2 * qb + g) * Q_BYTES);
           const uint64_t bd = make_smem_desc<false>(sKV + st * KV_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, ad + 2 * k, bd + 2 * k, idesc_qk, k > 0);
-          tcgen05_commit(s_full(g));
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, ad + 2 * k, bd + 2 * k, idesc_qk, k > 0);
+            tcgen05_commit(s_full(g));
+          }
+          __syncwarp();
         };
         for (int wi = blockIdx.x; decode_item(a, wi, it); wi += gridDim.x, ++item) {
           const int qb = item & 1;
@@ -186,22 +197,27 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_ts_kernel(const __grid_consta
                 mbar_wait(s_read(g), pcount & 1);                            // S_g(j) is in the group's registers: S_g is free
                 issue_qk(qb, nstage);                                        // runs under the group's exponentials of tile j
               } else {
-                tcgen05_commit(q_empty(qb));                                 // every Q K^T of this group has been issued
+                if (elect_one()) tcgen05_commit(q_empty(qb));                // every Q K^T of this group has been issued
+                __syncwarp();
               }
               mbar_wait(p_full(g), pcount & 1);                              // P_g(j) is in tensor memory
               ++pcount;
               if (j == 0 && item > 0) mbar_wait(o_free(g), (item - 1) & 1);    // previous item's O_g has been read out
               tcgen05_fence_after();
               const uint64_t vd = make_smem_desc<true>(sKV + stage * KV_BYTES + K_BYTES);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BKV / 16; ++k)
-                umma_bf16_ts(tO, tP + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-              tcgen05_commit(o_done(g));
-              tcgen05_commit(kv_empty(stage));                               // my MMAs on K_j / V_j (the other issuer adds its own)
+                for (int k = 0; k < BKV / 16; ++k)
+                  umma_bf16_ts(tO, tP + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                tcgen05_commit(o_done(g));
+                tcgen05_commit(kv_empty(stage));                             // my MMAs on K_j / V_j (the other issuer adds its own)
+              }
+              __syncwarp();
             } else {
               // a tile only the other group uses: wait until it has landed so the arrival lands in the right phase
               mbar_wait(kv_full(stage), kv_phase);
-              mbar_arrive(kv_empty(stage));
+              if (elect_one()) mbar_arrive(kv_empty(stage));
+              __syncwarp();
             }
             stage = nstage;
             kv_phase = nphase;

@@ -159,7 +159,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs)
-    if (lane == 0) {
+    {                                                   // whole warp (uniform operands), one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       int m0, n0, kb0, kb1;
@@ -169,8 +169,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           const uint32_t lead_full = mapa(full_bar(stage), lead_crank);
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
           const int k0 = kb * BK;
+          if (elect_one()) {
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
           if constexpr (CL == 1) {
             if constexpr (!A_MN) {
               tma_load_2d_pair(sa, &tma_a, lead_full, k0, m0 + (int)rank * BM);                 // my 128 rows of A
@@ -197,13 +198,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             for (int i = 0; i < BN / 2 / 64; ++i)                                               // my 2 x 64 columns of B
               tma_load_2d_pair(sb + i * 8192, &tma_b, lead_full, n0 + (int)rank * (BN / 2) + 64 * i, k0);
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // the WHOLE warp runs the loop (all values warp-uniform -> uniform registers, no per-instruction waterfall); one
+    // elected lane issues the tcgen05 instructions
+    if (leader) {
       constexpr uint32_t idesc = make_idesc(2 * BM, BN, A_MN, B_MN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -218,14 +223,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint64_t adesc = make_smem_desc<A_MN>(sa);
           const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * (A_MN ? (2048 >> 4) : 2)),
-                           bdesc + (uint64_t)(k * (B_MN ? (2048 >> 4) : 2)), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          tcgen05_commit_pair(empty_bar(stage), ALL_CTAS);      // frees the stage in every CTA of the cluster
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * (A_MN ? (2048 >> 4) : 2)),
+                             bdesc + (uint64_t)(k * (B_MN ? (2048 >> 4) : 2)), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            tcgen05_commit_pair(empty_bar(stage), ALL_CTAS);    // frees the stage in every CTA of the cluster
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit_pair(tfull_bar(acc), (uint16_t)(3u << (2 * pidx)));   // accumulators of both CTAs of MY pair are complete
+        if (elect_one()) tcgen05_commit_pair(tfull_bar(acc), (uint16_t)(3u << (2 * pidx)));   // accumulators of both CTAs of MY pair are complete
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -224,6 +224,16 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 1.0f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
 }
+// One lane of a CONVERGED warp (the lowest active one: lane 0 when all 32 are there).  The MMA / TMA roles run their loops
+// with the whole warp and predicate only the tcgen05 / bulk-copy instructions on this: descriptors and addresses are then
+// warp-uniform values and ptxas keeps them in uniform registers.  Inside `if (lane == 0) { loop }` every operand is
+// treated as per-thread and each UTCHMMA is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall — measured 117
+// cycles per MMA instruction regardless of its shape (scripts/ubench/attn_ubench.cu), against 35-115 when uniform.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 template <int REGS> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
