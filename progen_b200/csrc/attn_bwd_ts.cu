@@ -260,6 +260,35 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_ts_kernel(const __grid_co
     const float2 sc2 = make_float2(sc, sc);
     uint32_t x = 0, item = 0;
     KItem it;
+    // The item's accumulators are read out ONE OWN STEP LATE: after its last step a group goes straight on to the next
+    // item (whose scores are already there) and stores the previous item's dK / dV only after that step's P^T / dS^T have
+    // been published.  Waiting for the accumulate MMAs of the last step + the epilogue at every item boundary cost 21-28 %
+    // of the element-wise warps' time (ncu on the first version of this kernel).
+    bool pending = false;
+    int pend_b = 0, pend_hh = 0, pend_k0 = 0;
+    uint32_t pend_item = 0;
+    auto epilogue = [&]() {     // group 0 stores dK (x 1/sqrt(dh)), group 1 stores dV
+      mbar_wait(acc_full, pend_item & 1);
+      tcgen05_fence_after();
+      const long long tr = (long long)pend_b * a.n + pend_k0 + row;
+      bf16* out = a.dqkv + tr * (3LL * I) + (g == 0 ? I : 2 * I) + pend_hh * DH;
+      const uint32_t src = tmem_base + lane_addr + (g == 0 ? 384 : 448);
+      const float mul = g == 0 ? SCALE : 1.f;
+      uint32_t r0[32], r1[32];
+      tmem_ld32_issue(src, r0);
+      tmem_ld32_issue(src + 32, r1);
+      tmem_ld32_wait(r0);
+      tmem_ld32_wait(r1);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      float v0[32], v1[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]) * mul; v1[i] = __uint_as_float(r1[i]) * mul; }
+      store_grad_row(a, out, pend_k0 + row, 0, v0);
+      store_grad_row(a, out + 32, pend_k0 + row, 32, v1);
+      pending = false;
+    };
     for (int wi = blockIdx.x; decode_kitem(a, wi, it); wi += gridDim.x, ++item) {
       const int kj = it.j0 + row;                                            // in-window offset of this thread's key row
       for (int t = 0; t < it.nT; ++t, ++x) {
@@ -306,28 +335,11 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dkv_ts_kernel(const __grid_co
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(x % NB));
+        if (pending) epilogue();                                             // the PREVIOUS item's dK / dV (see above)
       }
-      // the item's accumulators: group 0 stores dK (x 1/sqrt(dh)), group 1 stores dV
-      mbar_wait(acc_full, item & 1);
-      tcgen05_fence_after();
-      const long long tr = (long long)it.b * a.n + it.k0 + row;
-      bf16* out = a.dqkv + tr * (3LL * I) + (g == 0 ? I : 2 * I) + it.hh * DH;
-      const uint32_t src = tmem_base + lane_addr + (g == 0 ? 384 : 448);
-      const float mul = g == 0 ? SCALE : 1.f;
-      uint32_t r0[32], r1[32];
-      tmem_ld32_issue(src, r0);
-      tmem_ld32_issue(src + 32, r1);
-      tmem_ld32_wait(r0);
-      tmem_ld32_wait(r1);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-      float v0[32], v1[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]) * mul; v1[i] = __uint_as_float(r1[i]) * mul; }
-      store_grad_row(a, out, it.k0 + row, 0, v0);
-      store_grad_row(a, out + 32, it.k0 + row, 32, v1);
+      pend_b = it.b; pend_hh = it.hh; pend_k0 = it.k0; pend_item = item; pending = true;
     }
+    if (pending) epilogue();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -444,20 +456,33 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_ts_kernel(const __grid_con
         auto issue_ahead = [&]() {
           if (!ahead.valid) return;
           const int qb = ahead.item & 1, st = xa % NS, buf = xa % NB;
-          if (ahead.t == 0) mbar_wait(qd_full(qb), (ahead.item >> 1) & 1);
+          if (ahead.t == 0) {
+            // the item's Q and dO tiles go to tensor memory ONCE (tcgen05.cp, behind every MMA of the previous item): S and dP
+            // then read their A operand there — an SS MMA spends ~32 cycles per K step just fetching 128 x 16 of A from
+            // shared memory (ubench: 83 vs 50 cycles per 128 x 64 x 16 instruction)
+            mbar_wait(qd_full(qb), (ahead.item >> 1) & 1);
+            tcgen05_fence_after();
+            const uint64_t qd = make_smem_desc<false>(sQD + (2 * qb) * ROW_TILE_BYTES);
+            const uint64_t dod = make_smem_desc<false>(sQD + (2 * qb + 1) * ROW_TILE_BYTES);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < DH / 16; ++k) tmem_cp_128x256b(tmem_base + 448 + 8 * k, qd + 2 * k);
+#pragma unroll
+              for (int k = 0; k < DH / 16; ++k) tmem_cp_128x256b(tmem_base + 480 + 8 * k, dod + 2 * k);
+              tcgen05_commit(qd_empty(qb));                                  // the shared-memory tiles are free once copied
+            }
+            __syncwarp();
+          }
           mbar_wait(kv_full(st), (xa / NS) & 1);
           tcgen05_fence_after();
-          const uint64_t qd = make_smem_desc<false>(sQD + (2 * qb) * ROW_TILE_BYTES);
-          const uint64_t dod = make_smem_desc<false>(sQD + (2 * qb + 1) * ROW_TILE_BYTES);
           const uint64_t kd = make_smem_desc<false>(sKV + st * STAGE_BYTES), vd = make_smem_desc<false>(sKV + st * STAGE_BYTES + COL_TILE_BYTES);
           const uint32_t tm = tmem_base + buf * 128;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < DH / 16; ++k) umma_bf16(tm, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < DH / 16; ++k) umma_bf16_ts(tm, tmem_base + 448 + 8 * k, kd + 2 * k, idesc_s, k > 0);
 #pragma unroll
-            for (int k = 0; k < DH / 16; ++k) umma_bf16(tm + 64, dod + 2 * k, vd + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < DH / 16; ++k) umma_bf16_ts(tm + 64, tmem_base + 480 + 8 * k, vd + 2 * k, idesc_s, k > 0);
             tcgen05_commit(s_full(buf));
-            if (ahead.t == ahead.it.nT - 1) tcgen05_commit(qd_empty(qb));    // the item's Q / dO tiles have had their last reader
           }
           __syncwarp();
           advance(ahead);
@@ -523,6 +548,26 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_ts_kernel(const __grid_con
     const float2 sc2 = make_float2(sc, sc);
     uint32_t x = 0, item = 0;
     QItem it;
+    // the item's dQ is read out one own step late (see the dK/dV kernel): group g stores channels [32 g, 32 g + 32)
+    bool pending = false;
+    int pend_b = 0, pend_hh = 0, pend_q0 = 0;
+    uint32_t pend_item = 0;
+    auto epilogue = [&]() {
+      mbar_wait(acc_full, pend_item & 1);
+      tcgen05_fence_after();
+      uint32_t r0[32];
+      tmem_ld32_issue(tmem_base + lane_addr + 384 + g * 32, r0);
+      tmem_ld32_wait(r0);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      float v0[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v0[i] = __uint_as_float(r0[i]) * SCALE;
+      const long long t = (long long)pend_b * a.n + pend_q0 + row;
+      store_grad_row(a, a.dqkv + t * (3LL * I) + pend_hh * DH + g * 32, pend_q0 + row, g * 32, v0);
+      pending = false;
+    };
     for (int wi = blockIdx.x; decode_qitem(a, wi, it); wi += gridDim.x, ++item) {
       const int qi = it.i0 + row;                                            // in-window offset of this thread's query row
       const int rb = item & 1;
@@ -568,22 +613,11 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_dq_ts_kernel(const __grid_con
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(x % NB));
+        if (pending) epilogue();                                             // the PREVIOUS item's dQ
       }
-      // the item's dQ: group g stores channels [32 g, 32 g + 32)
-      mbar_wait(acc_full, item & 1);
-      tcgen05_fence_after();
-      uint32_t r0[32];
-      tmem_ld32_issue(tmem_base + lane_addr + 384 + g * 32, r0);
-      tmem_ld32_wait(r0);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-      float v0[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v0[i] = __uint_as_float(r0[i]) * SCALE;
-      const long long t = (long long)it.b * a.n + it.q0 + row;
-      store_grad_row(a, a.dqkv + t * (3LL * I) + it.hh * DH + g * 32, it.q0 + row, g * 32, v0);
+      pend_b = it.b; pend_hh = it.hh; pend_q0 = it.q0; pend_item = item; pending = true;
     }
+    if (pending) epilogue();
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -165,6 +165,12 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// shared memory -> tensor memory, 128 lanes x 256 bits (8 columns): the SAME matrix a K-major SS MMA reads as its 128 x 16
+// bf16 A operand of one K step (same descriptor, same +2 per K step), landing where a TS MMA expects its A operand.
+// Asynchronous, ordered with the tcgen05.mma / tcgen05.commit of the issuing thread.  cute: SM100_UTCCP_128dp256bit_1cta.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // registers -> tensor memory: thread (lane L of the warp's lane quarter) writes N consecutive 32-bit columns of its lane
 template <int N> __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[N]);
 template <> __device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const uint32_t (&r)[8]) {
