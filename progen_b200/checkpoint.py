@@ -1,7 +1,10 @@
 """File-system checkpoints with the reference's package layout and naming (progen_transformer/checkpoint.py:12-37,
 train.py:196-202): cloudpickle of {next_seq_index, params, optim_state, model_config, run_id} to ckpt_<unix>.pkl, newest =
-lexicographically last, keep-last-N.  `params` is the haiku-shaped nested dict of NumPy arrays, so checkpoints
-interchange with the reference once its jax arrays are converted to NumPy.  The GCS twin is out of scope (no network)."""
+lexicographically last, keep-last-N.  `params` is the haiku-shaped nested dict of NumPy arrays, so the PARAMETERS of a
+checkpoint interchange with the reference once its jax arrays are converted to NumPy.  `optim_state` does not: here it is
+{count, mu, nu, acc, every} (Trainer.optim_state), not optax's (ClipState, (ScaleByAdamState, ...), ApplyEvery) tuple —
+resuming a reference checkpoint re-initialises the optimizer state (train.py warns), and the reference cannot resume ours.
+The GCS twin is out of scope (no network)."""
 import os
 import time
 from functools import partial

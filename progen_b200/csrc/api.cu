@@ -19,7 +19,7 @@ const char* progen_version(void) { return "progen_b200 0.1.0 (sm_100a; tcgen05/T
 
 const char* progen_last_error(void) { return g_err; }
 
-long long progen_launch_count(void) { return (long long)g_progen_launches; }
+long long progen_launch_count(void) { return (long long)__atomic_load_n(&g_progen_launches, __ATOMIC_RELAXED); }
 
 // north_star: no CPU fallback, sm_100 only.  Returns 0 iff the current device can run every kernel in this library.
 int progen_device_check(void) {

@@ -36,10 +36,10 @@ void progen_set_error(const char* fmt, ...);
   } while (0)
 
 // every kernel launch is followed by PG_LAUNCH_CHECK(): it also feeds progen_launch_count() (bench.py's gpu_launches)
-extern unsigned long long g_progen_launches;
+extern unsigned long long g_progen_launches;   // statistics only (bench.py's gpu_launches); bumped atomically, never read by a kernel path
 #define PG_LAUNCH_CHECK()                 \
   do {                                    \
-    ++g_progen_launches;                  \
+    __atomic_fetch_add(&g_progen_launches, 1ull, __ATOMIC_RELAXED); \
     PG_CUDA(cudaPeekAtLastError());       \
   } while (0)
 

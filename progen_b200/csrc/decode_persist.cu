@@ -482,7 +482,7 @@ int launch_run(const progen_decode_run_t& r, cudaStream_t s) {
   const int grid = pg_num_sms();
   void* args[] = {(void*)&r};
   PG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(TPB), args, smem, s));
-  ++g_progen_launches;
+  __atomic_fetch_add(&g_progen_launches, 1ull, __ATOMIC_RELAXED);
   return PROGEN_OK;
 }
 

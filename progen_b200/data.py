@@ -2,8 +2,10 @@
 
 Tokens: `ord(c) + 1`, 0 is pad / BOS / EOS (data.py:76-88).  Training rows have the reference's output contract
 (data.py:64-70): uint16 `(B, seq_len + 1)`, a 0 (BOS) in front, `bytes + 1` truncated to seq_len, zero padded.
-The TFRecord/GCS reader itself is outside the hot path (tensorflow is not installable here); `synthetic_iterator`
-produces the uniform-random rows BASELINE.json measures on, `iterator_from_sequences` turns strings into rows."""
+`iterator_from_tfrecords_folder` reads the reference's GZIP TFRecord files without tensorflow (length-prefixed records
+with masked CRC32C, one bytes feature `seq` per tf.train.Example; data.py:25-72) — only the GCS source is out of scope;
+`synthetic_iterator` produces the uniform-random rows BASELINE.json measures on, `iterator_from_sequences` turns strings
+into rows."""
 import numpy as np
 
 

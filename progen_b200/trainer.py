@@ -219,6 +219,11 @@ class Trainer:
 
     def load_optim_state(self, st):
         e = self.eng
+        if not (isinstance(st, dict) and {'count', 'mu', 'nu', 'acc'} <= set(st)):
+            # e.g. an optax chain state from a reference checkpoint: only `params` interchange (checkpoint.py)
+            import warnings
+            warnings.warn('optim_state is not a progen_b200 Trainer state (reference / optax checkpoint?): optimizer state re-initialised')
+            return
         self.count = int(st['count'])
         for buf, tree in ((self.m, st['mu']), (self.v, st['nu']), (self.acc, st['acc'])):
             host = np.zeros(e.n_params_padded, np.float32)

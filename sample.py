@@ -37,10 +37,13 @@ def main(seed, checkpoint_path, prime, greedy, mixed_precision, no_kv_cache):
         sampled = sample(seed, model.apply, params, prime_tensor, seq_len, top_k=25, add_bos=True, greedy=greedy)
     else:
         import torch
-        from progen_b200.decode import Decoder
-        dec = Decoder(model.config, params, weights_dtype=torch.bfloat16 if mixed_precision else torch.float32)
+        from progen_b200.decode import BatchDecoder
+        # one persistent kernel generates the whole sequence (csrc/decode_persist.cu).  With the reference's default
+        # --prime '' the reference draws position 0 from logits[-1] of the all-pad sequence; the cached decoder keeps the
+        # pad there (use --no_kv_cache for that exact behaviour).
+        dec = BatchDecoder(model.config, params, batch=1, weights_dtype=torch.bfloat16 if mixed_precision else torch.float32)
         sampled, steps, secs = dec.sample(prime_tensor, top_k=25, add_bos=True, greedy=greedy, seed=seed)
-        print(f'decoded {steps} tokens at {steps / max(secs, 1e-9):.0f} tokens/s (device time, KV-cached)')
+        print(f'decoded {steps} tokens at {steps / max(secs, 1e-9):.0f} tokens/s (device time, KV-cached persistent kernel)')
     print('\n', prime, '\n', '*' * 40, '\n', decode_tokens(sampled[prime_length:]))
 
 
