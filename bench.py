@@ -583,6 +583,9 @@ def main():
                                         sample=f'{rows} sequence x {n} tokens per step, fwd+bwd fp32, {timed} timed steps of {sec:.2f} s')
         print(json.dumps(line), flush=True)
     if world > 1:
+        # drop the captured graph (it references the communicator) before tearing NCCL down
+        tr._graph = None
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

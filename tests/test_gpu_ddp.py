@@ -20,7 +20,7 @@ def test_two_rank_trainer_equals_single_process(mp):
     env = dict(os.environ, DDP_TEST_MP='1' if mp else '0', NCCL_DEBUG='WARN')
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', str(port), os.path.join(ROOT, 'tests', 'ddp_worker.py')], capture_output=True, text=True,
-                       env=env, timeout=600)
+                       env=env, timeout=240)
     line = next((l for l in r.stdout.splitlines() if l.startswith('DDP_RESULT ')), None)
     assert line is not None, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(line[len('DDP_RESULT '):])

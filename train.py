@@ -148,6 +148,12 @@ def main(seed, batch_size, grad_accum_every, learning_rate, weight_decay, data_p
             print(prime_str, '\n', '*' * 40, '\n', decode_tokens(sampled[prime_length:]))
     if rank == 0:
         print(f'tokens/sec (host clock, incl. logging syncs): {tokens / max(1e-9, time.time() - t0):.0f}')
+    if world > 1:
+        import torch.distributed as dist
+        trainer._graph = None                      # a captured step references the communicator: drop it before NCCL goes away
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
