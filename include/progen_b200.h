@@ -219,13 +219,15 @@ typedef struct progen_decode_run_t {
   float* x;                    /* [B, d] residual stream */
   float* q;                    /* [B, inner] */
   float* att;                  /* [B, inner] */
-  float* att_part;             /* [B, heads, ceil(2*window/32), dim_head + 2] partial (max, sum, out) per 32-key slice */
+  float* att_part;             /* [B, heads, ceil(2*window/32), dim_head + 4] partial (max, sum, -, -, out) per 32-key slice */
   int32_t* att_count;          /* [B, heads] */
   float* u;                    /* [B, hid] */
-  float* sg;                   /* [B, hid/2] */
+  float* sg;                   /* [8, B, hid/2] partial spatial gates (up to 8 splits of the history range) */
   float* pj;                   /* [B, hid/2] */
   float* logits;               /* [B, V] */
   uint32_t* grid_bar;          /* grid barrier counter */
+  long long* prof;             /* optional [2][160][2] clock64 at entry / exit of every grid barrier of the launch's last
+                                  step, for CTA 0 and the last CTA, then [160][8] marks inside CTA 0's phases (NULL: off) */
 } progen_decode_run_t;
 
 int progen_decode_run(const progen_decode_run_t* run, void* stream);

@@ -4,27 +4,55 @@
 // HBM roofline, pure launch latency.  Here one cooperative kernel (one CTA per SM) generates every position of the
 // launch: the phases of a layer (LN + shift + QKV + rotary + cache | windowed attention | out-proj + residual | LN + shift +
 // FF-in + GLU/GELU | [gMLP: gate LN + causal spatial mix | SGU proj] | FF-out + residual) are separated by a grid barrier
-// (one atomic + one acquire poll per CTA), the weights stream through every SM's warps with 16-byte loads, and the token
-// loop, the sampler (top-k filter that keeps k-1 and zeroes the rest, Gumbel-max, `seq[pos+1] += id` — quirks Q5/Q6)
-// and the position counter stay on the device: no host round trip, no launches.
+// (one atomic + one acquire poll per CTA), and the token loop, the sampler (top-k filter that keeps k-1 and zeroes the
+// rest, Gumbel-max, `seq[pos+1] += id` — quirks Q5/Q6) and the position counter stay on the device: no host round trip.
 //
-// BATCH: `B` sequences advance in lock step ([B, 1] rows per step).  Every weight chunk a lane loads is used against all B
-// activation rows (staged in shared memory), partial sums are reduced across lanes with a transposing butterfly (31
-// shuffles per 32 values), so the step streams the weights ONCE for all sequences: decode throughput scales with B until
-// the FMA pipe, not HBM, is the bound.  Sequence b samples position p+1 iff p+1 >= start[b] (its prime is kept before).
+// A position is ~65 dependent phases, so single-stream speed is LATENCY: every global load that does not depend on the
+// previous phase's output (the CTA's slice of the weights, biases, LN scales, rotary entries, the residual it will add to)
+// is issued BEFORE the grid barrier that precedes the phase and waited for after it; what is left on the critical path is
+// one L2 round trip for the activations, two block reductions (LN), the FMAs and the barrier itself.
+//
+// BATCH: `B` sequences advance in lock step ([B, 1] rows per step) and the step streams the weights ONCE for all of them.
+// B <= 8: a lane holds 8 weights of two rows and multiplies them with every staged activation row (reduction over lanes).
+// B > 8: lane = sequence — the CTA's weight slice is staged in shared memory as fp32 and read with broadcast loads, each
+// lane keeps 32 activations of its sequence in registers and accumulates its warp's rows, so the FMA pipe, not
+// shared-memory bandwidth, is the bound.  Sequence b samples position p+1 iff p+1 >= start[b] (its prime is kept before).
 #include "common.cuh"
 #include "../../include/progen_b200.h"
 
 namespace {
 
 constexpr int TPB = 256, WPB = TPB / 32;
-constexpr int KC = 512;                 // activation columns staged per pass
+constexpr int MAXSEG = 4;               // (row pair, 256-column segment) units of weights a warp holds in registers
+constexpr int WSEGS = WPB * MAXSEG;     // segment slots of one CTA per wave
+constexpr int MAXEV = 160;              // profile events per sampled CTA (grid barriers of one step)
+constexpr int MAXSPLIT = 8;             // SGU: most splits of the history range
+template <int BT> struct Tile {         // activation columns staged per pass, by batch tile (shared memory [BT][XP])
+  static constexpr bool LANEB = BT > 8;                       // lane = sequence formulation
+  static constexpr int KCB = BT == 1 ? 8192 : (BT <= 8 ? 2048 : 512);
+  static constexpr int XP = LANEB ? KCB + 4 : KCB;            // row pitch (LANEB: +4 floats -> conflict-free float4 per lane)
+  static constexpr int BTP = BT | 1;                          // odd row pitch of the partial-sum scratch
+  static constexpr int STATF = (2 * BT + 2 * WPB + 3) & ~3;   // LN statistics [BT][2] + two block-reduction scratches
+  static constexpr int WSM = LANEB ? WSEGS * 512 : 0;         // LANEB: fp32 copy of one wave's weights [2 * PW rows][256 * KS]
+  static constexpr int PART = LANEB ? 0 : WSEGS * 2 * BTP;    // partial sums of the K segments
+  static constexpr int NBG = LANEB ? BT / 32 : 1;             // LANEB: 32-sequence groups; warp = (group, row split)
+  static constexpr int NRQ = WPB / NBG;
+  static constexpr int MAXLP = (WSEGS + NRQ - 1) / NRQ;       // pairs of a wave per row split
+};
 
 // ------------------------------------------------------------------------------------------------ grid barrier
-// monotonic counter: every CTA adds 1, then polls until all gridDim.x arrivals of this round are in
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round) {
+// monotonic counter: every CTA adds 1, then polls until all gridDim.x arrivals of this round are in.  `prof` (optional):
+// CTA 0 and the last CTA record clock64 at entry and exit of every barrier of the launch's LAST step.
+struct Prof { long long* buf; int ev; bool on; };
+// CTA 0, thread 0: clock64 at point k (< 8) inside the phase that ends with barrier number pf.ev  (buf + 4 * MAXEV: [MAXEV][8])
+__device__ __forceinline__ void prof_mark(const Prof& pf, int k) {
+  if (pf.on && blockIdx.x == 0 && threadIdx.x == 0 && pf.ev < MAXEV) pf.buf[4 * MAXEV + pf.ev * 8 + k] = clock64();
+}
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round, Prof& pf) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    long long t0 = 0;
+    if (pf.on) t0 = clock64();
     ++round;
     __threadfence();
     atomicAdd(bar, 1u);
@@ -33,32 +61,38 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
     } while (v < target);
+    if (pf.on && pf.ev < MAXEV) {
+      long long* e = pf.buf + ((blockIdx.x == 0 ? 0 : 1) * MAXEV + pf.ev) * 2;
+      e[0] = t0; e[1] = clock64();
+      ++pf.ev;
+    }
   }
   __syncthreads();
 }
 
-// sum over the 32 lanes of v[i], result for index i lands in lane i (v[0] of that lane)
-template <int N> __device__ __forceinline__ void xreduce(float (&v)[32], int lane) {
-  constexpr int H = N / 2;
-  const bool up = (lane & H) != 0;
+// 8 consecutive weights of a row as one lane's registers: bf16 = one 16-byte load, fp32 = two
+template <typename TW> struct W8 { uint4 q[sizeof(TW) / 2]; };
+template <typename TW> __device__ __forceinline__ void w8_load(W8<TW>& w, const TW* p) {
 #pragma unroll
-  for (int i = 0; i < H; ++i) {
-    const float send = up ? v[i] : v[i + H];
-    const float keep = up ? v[i + H] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
-  }
+  for (int i = 0; i < (int)(sizeof(TW) / 2); ++i) w.q[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
 }
-__device__ __forceinline__ float xreduce32(float (&v)[32], int lane) {
-  xreduce<32>(v, lane); xreduce<16>(v, lane); xreduce<8>(v, lane); xreduce<4>(v, lane); xreduce<2>(v, lane);
-  return v[0];
+template <typename TW> __device__ __forceinline__ void w8_zero(W8<TW>& w) {
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(TW) / 2); ++i) w.q[i] = make_uint4(0u, 0u, 0u, 0u);
 }
-
-template <typename TW> __device__ __forceinline__ void load_w8(const TW* p, float (&w)[8]);
-template <> __device__ __forceinline__ void load_w8<float>(const float* p, float (&w)[8]) { load_vec<8>(p, w); }
-template <> __device__ __forceinline__ void load_w8<bf16>(const bf16* p, float (&w)[8]) { load_vec<8>(p, w); }
+__device__ __forceinline__ void w8_unpack(const W8<bf16>& w, float (&f)[8]) {
+  const uint32_t u[4] = {w.q[0].x, w.q[0].y, w.q[0].z, w.q[0].w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(u[i] << 16); f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void w8_unpack(const W8<float>& w, float (&f)[8]) {
+  f[0] = __uint_as_float(w.q[0].x); f[1] = __uint_as_float(w.q[0].y); f[2] = __uint_as_float(w.q[0].z); f[3] = __uint_as_float(w.q[0].w);
+  f[4] = __uint_as_float(w.q[1].x); f[5] = __uint_as_float(w.q[1].y); f[6] = __uint_as_float(w.q[1].z); f[7] = __uint_as_float(w.q[1].w);
+}
+template <typename TW> struct WRegs { W8<TW> a[MAXSEG], c[MAXSEG]; };
 
 enum { EP_BIAS = 0, EP_ROTARY_CACHE = 1, EP_RESIDUAL = 2, EP_GLU = 3, EP_GELU = 4 };
-enum { PRO_NONE = 0, PRO_LN = 1 };
+enum { PRO_NONE = 0, PRO_LN = 1, PRO_ATT = 2, PRO_SGU = 3 };
 
 struct Phase {
   const void* wt;          // [N(,x2 for GLU), K]
@@ -70,37 +104,256 @@ struct Phase {
   int N, K;
   int epi;
   // prologue
-  int pro;                 // PRO_LN: x <- shift(LN(x) * scale)
+  int pro;                 // PRO_LN: x <- shift(LN(x) * scale); PRO_ATT: x <- merged attention partials (B = 1);
+                           // PRO_SGU: x <- xin * sum of the SGU partial gates
   const float* ln_scale;
   float* ln_prev;          // [B][2][K/2] token-shift state (read [pos&1], write [(pos+1)&1]); null: no shift
+  const float* aux;        // PRO_ATT: att_part; PRO_SGU: partial gates [nsplit][B][K]
+  int window, nsplit;
   // rotary / cache epilogue
   float* kcache; float* vcache; int inner, dim_head, n;
   const float* rot_sin; const float* rot_cos;
   int pos;
 };
 
-// One GEMV / skinny-GEMM phase over all B sequences.  BT = compile-time batch tile (B <= BT).
-template <int BT, typename TW>
-__device__ void gemv_phase(const Phase& ph, int B, float* xs /* smem [BT][KC] */, float* red /* smem scratch */) {
+// values a thread needs in a phase that do NOT depend on the previous phase: loaded before the barrier (BT == 1 only)
+struct Pre { float b0, b1, o0, o1, sn, cs; float4 sc, pv; };
+
+// Work split of one GEMV phase: CTA c owns the output row PAIRS [c*P/G, (c+1)*P/G) (pair = rows 2p, 2p+1, or p, p+N for
+// GLU), cut along K into 256-column segments; a wave is PW pairs x KS segments <= WSEGS slots, slot s -> warp s % WPB.
+struct Geo { int p_lo, np, KS, PW, nwaves; };
+__device__ __forceinline__ Geo phase_geo(const Phase& ph) {
+  const int npairs = ph.epi == EP_GLU ? ph.N : ph.N >> 1;
+  Geo g;
+  g.p_lo = (int)((long long)blockIdx.x * npairs / gridDim.x);
+  g.np = (int)((long long)(blockIdx.x + 1) * npairs / gridDim.x) - g.p_lo;
+  g.KS = (ph.K + 255) >> 8;
+  g.PW = WSEGS / g.KS;
+  g.nwaves = (g.np + g.PW - 1) / g.PW;
+  return g;
+}
+
+// Issue the 16-byte loads of one wave's weights (no use of the data here: the caller may put a grid barrier and other
+// phases between this and the FMAs, so HBM / L2 latency overlaps the barrier).
+template <typename TW>
+__device__ __forceinline__ void load_wave(const Phase& ph, const Geo& g, int wave, WRegs<TW>& w) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TW* W = reinterpret_cast<const TW*>(ph.wt);
-  const int npairs = ph.epi == EP_GLU ? ph.N : ph.N / 2;
-  const int total_warps = gridDim.x * WPB;
-  const int gw = blockIdx.x * WPB + warp;
-  const int rounds = (npairs + total_warps - 1) / total_warps;
-  const int nchunks = (ph.K + KC - 1) / KC;
-  // LN statistics of every sequence's row (whole K), once per phase: warp b % WPB handles row b
-  float* stat = red;                       // [BT][2]
-  if (ph.pro == PRO_LN) {
+  const int pbase = wave * g.PW;
+  const int pw = min(g.PW, g.np - pbase);
+#pragma unroll
+  for (int i = 0; i < MAXSEG; ++i) {
+    const int sw = warp + WPB * i;
+    const int pl = sw / g.KS, ks = sw - pl * g.KS;
+    const int k = ks * 256 + lane * 8;
+    if (pl < pw && k < ph.K) {
+      const int pair = g.p_lo + pbase + pl;
+      const long long r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+      w8_load<TW>(w.a[i], W + r0 * ph.K + k);
+      w8_load<TW>(w.c[i], W + r1 * ph.K + k);
+    } else {
+      w8_zero<TW>(w.a[i]);
+      w8_zero<TW>(w.c[i]);
+    }
+  }
+}
+
+// everything of phase `ph` (pos filled in) that can be loaded before the barrier in front of it
+template <int BT, typename TW>
+__device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pre& pre) {
+  const Geo g = phase_geo(ph);
+  load_wave<TW>(ph, g, 0, w);
+  if constexpr (BT == 1) {
+    const int t = threadIdx.x;
+    if (t < min(g.PW, g.np)) {                                  // this thread finalizes pair t of wave 0
+      const int pair = g.p_lo + t;
+      const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+      pre.b0 = ph.bias ? ph.bias[r0] : 0.f;
+      pre.b1 = ph.bias ? ph.bias[r1] : 0.f;
+      if (ph.epi == EP_RESIDUAL) { pre.o0 = __ldcg(ph.out + r0); pre.o1 = __ldcg(ph.out + r1); }
+      if (ph.epi == EP_ROTARY_CACHE) {
+        const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
+        pre.sn = ph.rot_sin[ph.pos * hd + j]; pre.cs = ph.rot_cos[ph.pos * hd + j];
+      }
+    }
+    const int k = t * 4;
+    if (ph.pro == PRO_LN && k < ph.K && ph.K <= 4 * TPB) {
+      pre.sc = *reinterpret_cast<const float4*>(ph.ln_scale + k);
+      if (ph.ln_prev && k < (ph.K >> 1)) pre.pv = __ldcg(reinterpret_cast<const float4*>(ph.ln_prev + (ph.pos & 1) * (ph.K >> 1) + k));
+    }
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch /* [WPB] */) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < WPB; ++k) t += scratch[k];
+  return t;
+}
+
+// shared-memory position of activation column k (k % 4 == 0) of a staged row.  B <= 8: the two 16-byte halves of every
+// 8-column group live in two planes, so the lanes of a warp (8 columns each) read consecutive 16-byte words.
+template <int BT> __device__ __forceinline__ int xs_off(int k) {
+  if constexpr (Tile<BT>::LANEB) return k;
+  else return ((k >> 2) & 1) * (Tile<BT>::KCB / 2) + (k >> 3) * 4;
+}
+
+// merged attention output of (sequence 0, columns k..k+3) from the per-slice partials (B = 1: the out-proj phase merges)
+__device__ __forceinline__ float4 merge_att(const Phase& ph, int k) {
+  const int dh = ph.dim_head, w = ph.window;
+  const int win = ph.pos / w, i = ph.pos % w;
+  const int nreal = (win > 0 ? w : 0) + i + 1;
+  const int nsl = (nreal + 31) / 32;
+  const int KS = (2 * w + 31) / 32;
+  const float* pb = ph.aux + (long long)(k / dh) * KS * (dh + 4);
+  const int c = k % dh;
+  float M = win == 0 ? 0.f : -INFINITY;               // zero look-back keys of window 0: logit 0 (quirk Q1)
+  float Lt = 0.f;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < nsl; s0 += 8) {
+    float2 ml[8];
+    float4 o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool on = s0 + u < nsl;
+      const float* pk = pb + (on ? s0 + u : 0) * (dh + 4);
+      ml[u] = __ldcg(reinterpret_cast<const float2*>(pk));
+      o[u] = __ldcg(reinterpret_cast<const float4*>(pk + 4 + c));
+      if (!on) ml[u] = make_float2(-INFINITY, 0.f);        // weight exp(-inf) = 0
+    }
+    float Mn = M;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Mn = fmaxf(Mn, ml[u].x);
+    const float fo = (M == -INFINITY) ? 0.f : expf(M - Mn);
+    Lt *= fo; a.x *= fo; a.y *= fo; a.z *= fo; a.w *= fo;
+    M = Mn;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float f = expf(ml[u].x - M);
+      Lt = fmaf(ml[u].y, f, Lt);
+      a.x = fmaf(f, o[u].x, a.x); a.y = fmaf(f, o[u].y, a.y); a.z = fmaf(f, o[u].z, a.z); a.w = fmaf(f, o[u].w, a.w);
+    }
+  }
+  if (win == 0) Lt += (float)w * expf(-M);
+  const float inv = 1.f / Lt;
+  return make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+}
+
+// One GEMV / skinny-GEMM phase over all B sequences.  BT = compile-time batch tile (B <= BT).  `w`, `pre` hold what
+// prefetch_phase loaded for THIS phase (the caller ran it before the previous grid barrier, or just now).
+template <int BT, typename TW>
+__device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, float* part, float* stat, float* wsm, WRegs<TW>& w, const Pre& pre, const Prof& pf) {
+  constexpr int KCB = Tile<BT>::KCB, XP = Tile<BT>::XP, BTP = Tile<BT>::BTP;
+  constexpr bool LANEB = Tile<BT>::LANEB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Geo g = phase_geo(ph);
+  const int nchunks = (ph.K + KCB - 1) / KCB;
+  const int half = ph.K >> 1;
+  bool staged = false;
+  if (BT == 1 && ph.K <= 4 * TPB) {
+    // single sequence, one float4 per thread: LN statistics, scale, token shift and the staging in one pass
+    const int k = threadIdx.x * 4;
+    const bool in = k < ph.K;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) {
+      if (ph.pro == PRO_ATT) t = merge_att(ph, k);
+      else t = __ldcg(reinterpret_cast<const float4*>(ph.xin + k));
+    }
+    if (ph.pro == PRO_SGU && in) {
+      float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < MAXSPLIT; ++s) {
+        if (s < ph.nsplit) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ph.aux + (long long)s * ph.K + k));
+          gsum.x += v.x; gsum.y += v.y; gsum.z += v.z; gsum.w += v.w;
+        }
+      }
+      t.x *= gsum.x; t.y *= gsum.y; t.z *= gsum.z; t.w *= gsum.w;
+    }
+    if (ph.pro == PRO_LN) {
+      const float mean = block_sum((t.x + t.y) + (t.z + t.w), stat + 2 * BT) / ph.K;
+      prof_mark(pf, 5);
+      const float a0 = t.x - mean, a1 = t.y - mean, a2 = t.z - mean, a3 = t.w - mean;
+      const float q = block_sum(in ? (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3) : 0.f, stat + 2 * BT + WPB);
+      prof_mark(pf, 6);
+      const float rstd = rsqrtf(q / ph.K + 1e-5f);
+      if (in) {
+        t.x = a0 * rstd * pre.sc.x; t.y = a1 * rstd * pre.sc.y; t.z = a2 * rstd * pre.sc.z; t.w = a3 * rstd * pre.sc.w;
+        if (ph.ln_prev && k < half) {
+          if (blockIdx.x == 0) *reinterpret_cast<float4*>(ph.ln_prev + ((ph.pos + 1) & 1) * half + k) = t;
+          t = pre.pv;
+        }
+      }
+    }
+    if (in) *reinterpret_cast<float4*>(xs + xs_off<BT>(k)) = t;
+    __syncthreads();
+    staged = true;
+  } else if (ph.pro == PRO_LN && nchunks == 1 && ph.K <= 1024) {
+    // whole rows fit one pass: warp per sequence, the row stays in registers between the statistics and the staging;
+    // two rows in flight per warp
+    for (int b0 = warp; b0 < B; b0 += 2 * WPB) {
+      float4 v[2][8];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int b = b0 + rr * WPB;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = j * 128 + lane * 4;
+          v[rr][j] = (b < B && k < ph.K) ? __ldcg(reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int b = b0 + rr * WPB;
+        if (b >= B) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += (v[rr][j].x + v[rr][j].y) + (v[rr][j].z + v[rr][j].w);
+        const float mean = warp_sum(s) / ph.K;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j * 128 + lane * 4 < ph.K) {
+            const float a0 = v[rr][j].x - mean, a1 = v[rr][j].y - mean, a2 = v[rr][j].z - mean, a3 = v[rr][j].w - mean;
+            q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / ph.K + 1e-5f);
+        float* st = ph.ln_prev ? ph.ln_prev + (long long)b * ph.K : nullptr;       // [2][K/2]
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = j * 128 + lane * 4;
+          if (k < ph.K) {
+            const float4 sc = *reinterpret_cast<const float4*>(ph.ln_scale + k);
+            float4 t;
+            t.x = (v[rr][j].x - mean) * rstd * sc.x; t.y = (v[rr][j].y - mean) * rstd * sc.y;
+            t.z = (v[rr][j].z - mean) * rstd * sc.z; t.w = (v[rr][j].w - mean) * rstd * sc.w;
+            if (st && k < half) {
+              const float4 pv = __ldcg(reinterpret_cast<const float4*>(st + (ph.pos & 1) * half + k));
+              if (blockIdx.x == 0) *reinterpret_cast<float4*>(st + ((ph.pos + 1) & 1) * half + k) = t;
+              t = pv;
+            }
+            *reinterpret_cast<float4*>(xs + b * XP + xs_off<BT>(k)) = t;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    staged = true;
+  } else if (ph.pro == PRO_LN) {
+    // LN statistics of every sequence's row (whole K), once per phase: warp b % WPB handles row b
     for (int b = warp; b < B; b += WPB) {
       const float* xr = ph.xin + (long long)b * ph.ldx;
       float s = 0.f;
-      for (int k = lane * 4; k < ph.K; k += 128) { const float4 t = *reinterpret_cast<const float4*>(xr + k); s += (t.x + t.y) + (t.z + t.w); }
+      for (int k = lane * 4; k < ph.K; k += 128) { const float4 t = __ldcg(reinterpret_cast<const float4*>(xr + k)); s += (t.x + t.y) + (t.z + t.w); }
       s = warp_sum(s);
       const float mean = s / ph.K;
       float q = 0.f;
       for (int k = lane * 4; k < ph.K; k += 128) {
-        const float4 t = *reinterpret_cast<const float4*>(xr + k);
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(xr + k));
         const float a0 = t.x - mean, a1 = t.y - mean, a2 = t.z - mean, a3 = t.w - mean;
         q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
       }
@@ -109,109 +362,214 @@ __device__ void gemv_phase(const Phase& ph, int B, float* xs /* smem [BT][KC] */
     }
     __syncthreads();
   }
-  for (int rd = 0; rd < rounds; ++rd) {
-    const int pair = rd * total_warps + gw;
-    const bool active = pair < npairs;
-    int r0 = 0, r1 = 0;
-    if (active) {
-      if (ph.epi == EP_GLU) { r0 = pair; r1 = pair + ph.N; }
-      else { r0 = 2 * pair; r1 = r0 + 1; }
-    }
-    float acc0[BT], acc1[BT];
+  // stage x[:, k0 .. k0+kn) (with the prologue) into shared memory; four independent loads in flight per thread
+  auto stage = [&](int kc) {
+    const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
+    const int nvec = B * (kn >> 2);
+    for (int base = 0; base < nvec; base += 4 * TPB) {
+      float4 t[4];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
-    for (int kc = 0; kc < nchunks; ++kc) {
-      const int k0 = kc * KC, kn = min(KC, ph.K - k0);
-      // ---- stage x[:, k0 .. k0+kn) (with the LN + shift prologue) into shared memory
-      if (rd == 0 || nchunks > 1) {
-        __syncthreads();
-        const int half = ph.K >> 1;
-        for (int idx = threadIdx.x; idx < B * (kn >> 2); idx += TPB) {
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * TPB + threadIdx.x;
+        if (idx < nvec) {
           const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
-          float4 t = *reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k0 + k);
-          if (ph.pro == PRO_LN) {
-            const float mean = stat[2 * b], rstd = stat[2 * b + 1];
-            const float4 sc = *reinterpret_cast<const float4*>(ph.ln_scale + k0 + k);
-            t.x = (t.x - mean) * rstd * sc.x; t.y = (t.y - mean) * rstd * sc.y;
-            t.z = (t.z - mean) * rstd * sc.z; t.w = (t.w - mean) * rstd * sc.w;
-            if (ph.ln_prev && k0 + k < half) {
-              float* st = ph.ln_prev + (long long)b * ph.K;            // [2][K/2]
-              const float4 pv = *reinterpret_cast<const float4*>(st + (ph.pos & 1) * half + k0 + k);
-              if (blockIdx.x == 0) *reinterpret_cast<float4*>(st + ((ph.pos + 1) & 1) * half + k0 + k) = t;
-              t = pv;
+          t[u] = __ldcg(reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k0 + k));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * TPB + threadIdx.x;
+        if (idx >= nvec) continue;
+        const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
+        float4 v = t[u];
+        if (ph.pro == PRO_LN) {
+          const float mean = stat[2 * b], rstd = stat[2 * b + 1];
+          const float4 sc = *reinterpret_cast<const float4*>(ph.ln_scale + k0 + k);
+          v.x = (v.x - mean) * rstd * sc.x; v.y = (v.y - mean) * rstd * sc.y;
+          v.z = (v.z - mean) * rstd * sc.z; v.w = (v.w - mean) * rstd * sc.w;
+          if (ph.ln_prev && k0 + k < half) {
+            float* st = ph.ln_prev + (long long)b * ph.K;            // [2][K/2]
+            const float4 pv = __ldcg(reinterpret_cast<const float4*>(st + (ph.pos & 1) * half + k0 + k));
+            if (blockIdx.x == 0) *reinterpret_cast<float4*>(st + ((ph.pos + 1) & 1) * half + k0 + k) = v;
+            v = pv;
+          }
+        } else if (ph.pro == PRO_SGU) {
+          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s = 0; s < ph.nsplit; ++s) {
+            const float4 q = __ldcg(reinterpret_cast<const float4*>(ph.aux + ((long long)s * B + b) * ph.K + k0 + k));
+            gsum.x += q.x; gsum.y += q.y; gsum.z += q.z; gsum.w += q.w;
+          }
+          v.x *= gsum.x; v.y *= gsum.y; v.z *= gsum.z; v.w *= gsum.w;
+        }
+        *reinterpret_cast<float4*>(xs + b * XP + xs_off<BT>(k)) = v;
+      }
+    }
+  };
+  // bias + activation / residual / rotary + cache for the two rows of `pair` of sequence b
+  auto epilogue = [&](int b, int pair, float s0, float s1, bool pf /* operands in `pre` */) {
+    const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+    if (pf) { s0 += pre.b0; s1 += pre.b1; }
+    else if (ph.bias) { s0 += ph.bias[r0]; s1 += ph.bias[r1]; }
+    float* o = ph.out + (long long)b * ph.ldo;
+    if (ph.epi == EP_BIAS) { o[r0] = s0; o[r1] = s1; }
+    else if (ph.epi == EP_RESIDUAL) {
+      if (pf) { o[r0] = pre.o0 + s0; o[r1] = pre.o1 + s1; }
+      else { o[r0] = __ldcg(o + r0) + s0; o[r1] = __ldcg(o + r1) + s1; }
+    }
+    else if (ph.epi == EP_GELU) { o[r0] = gelu_tanh(s0); o[r1] = gelu_tanh(s1); }
+    else if (ph.epi == EP_GLU) { o[r0] = s0 * gelu_tanh(s1); }
+    else {  // EP_ROTARY_CACHE: rotary on q, k AND v (progen.py:87); k, v rows go to the caches at position pos
+      const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
+      const float sn = pf ? pre.sn : ph.rot_sin[ph.pos * hd + j], cs = pf ? pre.cs : ph.rot_cos[ph.pos * hd + j];
+      const float o0 = s0 * cs - s1 * sn, o1 = s1 * cs + s0 * sn;
+      const int sec = r0 / ph.inner, c = r0 % ph.inner;
+      float* dst = sec == 0 ? o + c
+                            : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)b * ph.n + ph.pos) * ph.inner + c;
+      dst[0] = o0; dst[1] = o1;
+    }
+  };
+  if (!staged && nchunks == 1) { stage(0); __syncthreads(); }
+  prof_mark(pf, 1);
+  for (int wave = 0; wave < g.nwaves; ++wave) {
+    if (wave > 0) load_wave<TW>(ph, g, wave, w);
+    const int pbase = wave * g.PW;
+    const int pw = min(g.PW, g.np - pbase);
+    if constexpr (!LANEB) {
+      for (int kc = 0; kc < nchunks; ++kc) {
+        if (nchunks > 1) { __syncthreads(); stage(kc); __syncthreads(); }
+        const int k0 = kc * KCB;
+#pragma unroll
+        for (int i = 0; i < MAXSEG; ++i) {
+          const int sw = warp + WPB * i;
+          const int pl = sw / g.KS, ks = sw - pl * g.KS;
+          const int kseg = ks * 256;
+          if (pl >= pw || kseg < k0 || kseg >= k0 + KCB) continue;     // warp-uniform
+          const int k = kseg + lane * 8;
+          float acc0[BT], acc1[BT];
+#pragma unroll
+          for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+          if (k < ph.K) {
+            float a[8], c[8];
+            w8_unpack(w.a[i], a);
+            w8_unpack(w.c[i], c);
+            const float* xk = xs + xs_off<BT>(k - k0);
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+              if (b < B) {
+                const float4 x0 = *reinterpret_cast<const float4*>(xk + b * XP);
+                const float4 x1 = *reinterpret_cast<const float4*>(xk + b * XP + KCB / 2);
+                acc0[b] = fmaf(a[0], x0.x, fmaf(a[1], x0.y, fmaf(a[2], x0.z, fmaf(a[3], x0.w, acc0[b]))));
+                acc0[b] = fmaf(a[4], x1.x, fmaf(a[5], x1.y, fmaf(a[6], x1.z, fmaf(a[7], x1.w, acc0[b]))));
+                acc1[b] = fmaf(c[0], x0.x, fmaf(c[1], x0.y, fmaf(c[2], x0.z, fmaf(c[3], x0.w, acc1[b]))));
+                acc1[b] = fmaf(c[4], x1.x, fmaf(c[5], x1.y, fmaf(c[6], x1.z, fmaf(c[7], x1.w, acc1[b]))));
+              }
             }
           }
-          *reinterpret_cast<float4*>(xs + b * KC + k) = t;
-        }
-        __syncthreads();
-      }
-      if (!active) continue;
-      // ---- this warp's two weight rows against every staged activation row
-      const TW* w0 = W + (long long)r0 * ph.K + k0;
-      const TW* w1 = W + (long long)r1 * ph.K + k0;
-      for (int k = lane * 8; k < kn; k += 256) {
-        float a[8], c[8];
-        load_w8<TW>(w0 + k, a);
-        load_w8<TW>(w1 + k, c);
+          // reduce over lanes: lane b ends with sequence b's sums
+          float* p0 = part + (sw * 2) * BTP;
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          if (b < B) {
-            const float4 x0 = *reinterpret_cast<const float4*>(xs + b * KC + k);
-            const float4 x1 = *reinterpret_cast<const float4*>(xs + b * KC + k + 4);
-            acc0[b] = fmaf(a[0], x0.x, fmaf(a[1], x0.y, fmaf(a[2], x0.z, fmaf(a[3], x0.w, acc0[b]))));
-            acc0[b] = fmaf(a[4], x1.x, fmaf(a[5], x1.y, fmaf(a[6], x1.z, fmaf(a[7], x1.w, acc0[b]))));
-            acc1[b] = fmaf(c[0], x0.x, fmaf(c[1], x0.y, fmaf(c[2], x0.z, fmaf(c[3], x0.w, acc1[b]))));
-            acc1[b] = fmaf(c[4], x1.x, fmaf(c[5], x1.y, fmaf(c[6], x1.z, fmaf(c[7], x1.w, acc1[b]))));
+          for (int j = 0; j < BT; ++j) {
+            const float t0 = warp_sum(acc0[j]), t1 = warp_sum(acc1[j]);
+            if (lane == j) { s0 = t0; s1 = t1; }
+          }
+          if (lane < BT) { p0[lane] = s0; p0[BTP + lane] = s1; }
+        }
+      }
+      __syncthreads();
+      prof_mark(pf, 2);
+      // finalize this wave's pairs: sum the K segments in order, then the epilogue (threads run over pairs fastest, so
+      // the two adjacent output columns of neighbouring pairs coalesce)
+      for (int idx = threadIdx.x; idx < pw * B; idx += TPB) {
+        const int b = idx / pw, pl = idx - b * pw;
+        float s0 = 0.f, s1 = 0.f;
+        for (int ks = 0; ks < g.KS; ++ks) {
+          const float* pp = part + ((pl * g.KS + ks) * 2) * BTP + b;
+          s0 += pp[0]; s1 += pp[BTP];
+        }
+        epilogue(b, g.p_lo + pbase + pl, s0, s1, BT == 1 && wave == 0);
+      }
+      if (wave + 1 < g.nwaves) __syncthreads();
+    } else {
+      // ---- lane = sequence.  (1) this wave's weights -> shared memory as fp32 [row = 2*pl + which][256*KS columns]
+      constexpr int NBG = Tile<BT>::NBG, NRQ = Tile<BT>::NRQ, MAXLP = Tile<BT>::MAXLP;
+      const int WK = g.KS * 256;                             // columns per staged row (tail zero-filled by load_wave)
+      __syncthreads();                                       // the previous wave's / phase's readers of wsm are done
+#pragma unroll
+      for (int i = 0; i < MAXSEG; ++i) {
+        const int sw = warp + WPB * i;
+        const int pl = sw / g.KS, ks = sw - pl * g.KS;
+        if (pl >= g.PW) continue;
+        float a[8], c[8];
+        w8_unpack(w.a[i], a);
+        w8_unpack(w.c[i], c);
+        float* d0 = wsm + (2 * pl) * WK + ks * 256 + lane * 8;
+        *reinterpret_cast<float4*>(d0) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(d0 + 4) = make_float4(a[4], a[5], a[6], a[7]);
+        *reinterpret_cast<float4*>(d0 + WK) = make_float4(c[0], c[1], c[2], c[3]);
+        *reinterpret_cast<float4*>(d0 + WK + 4) = make_float4(c[4], c[5], c[6], c[7]);
+      }
+      // (2) warp = (32-sequence group, row split q): pairs q, q + NRQ, ... of the wave; 32 activations of the lane's
+      // sequence in registers against the warp's rows, weights by broadcast loads
+      const int bg = warp % NBG, q = warp / NBG;
+      const int b = bg * 32 + lane;
+      float acc[MAXLP][2][2];
+#pragma unroll
+      for (int lp = 0; lp < MAXLP; ++lp) { acc[lp][0][0] = acc[lp][0][1] = acc[lp][1][0] = acc[lp][1][1] = 0.f; }
+      for (int kc = 0; kc < nchunks; ++kc) {
+        __syncthreads();                                     // wsm written (kc == 0) / the previous chunk's xs readers done
+        if (nchunks > 1) { stage(kc); __syncthreads(); }
+        const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
+        const float* xrow = xs + (b < B ? b : 0) * XP;
+        for (int kb = 0; kb < kn; kb += 32) {
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(xrow + kb + j * 4);
+            x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+          }
+          const float* wk = wsm + k0 + kb;
+#pragma unroll
+          for (int lp = 0; lp < MAXLP; ++lp) {
+            const int pl = q + NRQ * lp;
+            if (pl < pw) {                                   // warp-uniform
+#pragma unroll
+              for (int wh = 0; wh < 2; ++wh) {
+                const float* wr = wk + (2 * pl + wh) * WK;
+                float e0 = acc[lp][wh][0], e1 = acc[lp][wh][1];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                  const float4 u0 = *reinterpret_cast<const float4*>(wr + j * 4);        // same address in every lane: broadcast
+                  const float4 u1 = *reinterpret_cast<const float4*>(wr + j * 4 + 4);
+                  e0 = fmaf(u0.x, x[4 * j], fmaf(u0.y, x[4 * j + 1], fmaf(u0.z, x[4 * j + 2], fmaf(u0.w, x[4 * j + 3], e0))));
+                  e1 = fmaf(u1.x, x[4 * j + 4], fmaf(u1.y, x[4 * j + 5], fmaf(u1.z, x[4 * j + 6], fmaf(u1.w, x[4 * j + 7], e1))));
+                }
+                acc[lp][wh][0] = e0; acc[lp][wh][1] = e1;
+              }
+            }
           }
         }
       }
-    }
-    if (!active) continue;
-    // ---- reduce over lanes; lane L ends with the sums of sequence (g * 32 + L), g = 0 .. BT/32-1  (BT < 32: all lanes hold b)
-    constexpr int NG = BT >= 32 ? BT / 32 : 1;
+      // (3) epilogue straight from the registers (lane = sequence)
+      if (b < B) {
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      float s0, s1;
-      int b;
-      if constexpr (BT >= 32) {
-        float v0[32], v1[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { v0[i] = acc0[g * 32 + i]; v1[i] = acc1[g * 32 + i]; }
-        s0 = xreduce32(v0, lane);
-        s1 = xreduce32(v1, lane);
-        b = g * 32 + lane;
-      } else {
-        s0 = 0.f; s1 = 0.f; b = lane;
-#pragma unroll
-        for (int i = 0; i < BT; ++i) {
-          const float t0 = warp_sum(acc0[i]), t1 = warp_sum(acc1[i]);
-          if (lane == i) { s0 = t0; s1 = t1; }
+        for (int lp = 0; lp < MAXLP; ++lp) {
+          const int pl = q + NRQ * lp;
+          if (pl < pw) epilogue(b, g.p_lo + pbase + pl, acc[lp][0][0] + acc[lp][0][1], acc[lp][1][0] + acc[lp][1][1], false);
         }
-      }
-      if (b >= B) continue;
-      if (ph.bias) { s0 += ph.bias[r0]; s1 += ph.bias[r1]; }
-      float* o = ph.out + (long long)b * ph.ldo;
-      if (ph.epi == EP_BIAS) { o[r0] = s0; o[r1] = s1; }
-      else if (ph.epi == EP_RESIDUAL) { o[r0] += s0; o[r1] += s1; }
-      else if (ph.epi == EP_GELU) { o[r0] = gelu_tanh(s0); o[r1] = gelu_tanh(s1); }
-      else if (ph.epi == EP_GLU) { o[r0] = s0 * gelu_tanh(s1); }
-      else {  // EP_ROTARY_CACHE: rotary on q, k AND v (progen.py:87); k, v rows go to the caches at position pos
-        const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
-        const float sn = ph.rot_sin[ph.pos * hd + j], cs = ph.rot_cos[ph.pos * hd + j];
-        const float o0 = s0 * cs - s1 * sn, o1 = s1 * cs + s0 * sn;
-        const int sec = r0 / ph.inner, c = r0 % ph.inner;
-        float* dst = sec == 0 ? o + c
-                              : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)b * ph.n + ph.pos) * ph.inner + c;
-        dst[0] = o0; dst[1] = o1;
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-// task = (sequence, head, slice of 32 keys): partial (m, l, o[dh]) -> att_part; the warp that finishes a (sequence, head)'s
-// last slice merges the partials (plus window 0's w zero keys with logit 0, quirk Q1) into att[b, head * dh ..].
-__device__ void attention_phase(const progen_decode_run_t& r, const progen_decode_layer_t& L, int pos, float* sq /* smem [WPB][dh] */) {
+// task = (sequence, head, slice of 32 keys), one warp: partial (m, l, o[dh]) -> att_part[(b, head)][slice][dh + 4].  All of
+// the task's K and V loads are independent of each other (lane = key for the logits; lane = (key group, 4 channels) for
+// the value sum), so a task is ONE memory round trip.  MERGE (B > 1): the warp that finishes a (sequence, head)'s last slice
+// merges the partials (plus window 0's w zero keys with logit 0, quirk Q1) into att[b, head * dh ..]; B = 1: the out-proj
+// phase merges while it stages its input (merge_att).
+template <bool MERGE, int NL /* lanes that cover one value row with float4 = dim_head / 4 */>
+__device__ void attention_phase_t(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq /* smem [WPB][dh] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = r.dim_head, w = r.window, I = r.inner;
   const int win = pos / w, i = pos % w;
@@ -219,262 +577,421 @@ __device__ void attention_phase(const progen_decode_run_t& r, const progen_decod
   const int nreal = (win > 0 ? w : 0) + i + 1;
   const int nsl = (nreal + 31) / 32;
   const int KS = (2 * w + 31) / 32;                         // slots per (b, head) in att_part
+  const int PS = dh + 4;                                    // floats per slot: m, l, -, -, o[dh]
   const int tasks = r.B * r.heads * nsl;
   const float scale = rsqrtf((float)dh);
+  constexpr int KG = 32 / NL;                               // key groups
+  constexpr int NH = NL >= 2 ? NL / 2 : 1;                  // value quads per lane and batch of loads
+  const int kg = lane / NL, c4 = (lane % NL) * 4;
   float* q_s = sq + warp * dh;
-  for (int t = blockIdx.x * WPB + warp; t < tasks; t += gridDim.x * WPB) {
+  for (int t = warp * gridDim.x + blockIdx.x; t < tasks; t += gridDim.x * WPB) {
     const int sl = t % nsl, bh = t / nsl, hh = bh % r.heads, b = bh / r.heads;
     const float* qv = r.q + (long long)b * I + hh * dh;
-    for (int c = lane; c < dh; c += 32) q_s[c] = qv[c];
     __syncwarp();
+    if (lane < NL) *reinterpret_cast<float4*>(q_s + lane * 4) = __ldcg(reinterpret_cast<const float4*>(qv + lane * 4));
     const int j = sl * 32 + lane;
     const bool valid = j < nreal;
-    const float* kr = L.kcache + ((long long)b * r.n + key0 + (valid ? j : 0)) * I + hh * dh;
+    const int nk = min(32, nreal - sl * 32);
+    const float* kr = kcache + ((long long)b * r.n + key0 + (valid ? j : 0)) * I + hh * dh;
+    const float* vb = vcache + ((long long)b * r.n + key0 + sl * 32) * I + hh * dh + c4;
+    // issue: the float4s of this lane's key row and the first half of this lane's value quads (keys kg, kg + KG, ...);
+    // the second half goes out as soon as the key registers are consumed
+    float4 kreg[NL], vreg[NH];
+#pragma unroll
+    for (int c = 0; c < NL; ++c) kreg[c] = __ldcg(reinterpret_cast<const float4*>(kr + c * 4));
+#pragma unroll
+    for (int jj = 0; jj < NH; ++jj) {
+      const int key = kg + jj * KG;
+      vreg[jj] = key < nk ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
     float s = 0.f;
-    for (int c = 0; c < dh; c += 4) {
-      const float4 kv = *reinterpret_cast<const float4*>(kr + c);
-      s = fmaf(kv.x, q_s[c], s); s = fmaf(kv.y, q_s[c + 1], s); s = fmaf(kv.z, q_s[c + 2], s); s = fmaf(kv.w, q_s[c + 3], s);
+#pragma unroll
+    for (int c = 0; c < NL; ++c) {
+      const float4 qq = *reinterpret_cast<const float4*>(q_s + c * 4);
+      s = fmaf(kreg[c].x, qq.x, s); s = fmaf(kreg[c].y, qq.y, s); s = fmaf(kreg[c].z, qq.z, s); s = fmaf(kreg[c].w, qq.w, s);
+    }
+    float4 vreg2[NH];
+#pragma unroll
+    for (int jj = 0; jj < NH; ++jj) {
+      const int key = kg + (jj + NH) * KG;
+      vreg2[jj] = (NH + jj < NL && key < nk) ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     s = valid ? s * scale : -INFINITY;
     const float m = warp_max(s);
     const float p = valid ? expf(s - m) : 0.f;
     const float l = warp_sum(p);
-    // o[c] = sum_j p_j v_j[c]: lanes own channels (c = lane, lane + 32, ...), p_j broadcast key by key
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    const int nk = min(32, nreal - sl * 32);
-    const float* vb = L.vcache + ((long long)b * r.n + key0 + sl * 32) * I + hh * dh;
-    for (int jj = 0; jj < nk; ++jj) {
-      const float pj = __shfl_sync(0xffffffffu, p, jj);
-      const float* vr = vb + (long long)jj * I;
-      if (lane < dh) o0 = fmaf(pj, vr[lane], o0);
-      if (lane + 32 < dh) o1 = fmaf(pj, vr[lane + 32], o1);
-      if (lane + 64 < dh) o2 = fmaf(pj, vr[lane + 64], o2);
-      if (lane + 96 < dh) o3 = fmaf(pj, vr[lane + 96], o3);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < NL; ++jj) {
+      const int key = kg + jj * KG;
+      const float pj = __shfl_sync(0xffffffffu, p, key & 31);                  // p = 0 for keys past the slice's end
+      const float4 vv = jj < NH ? vreg[jj % NH] : vreg2[jj % NH];
+      o.x = fmaf(pj, vv.x, o.x); o.y = fmaf(pj, vv.y, o.y); o.z = fmaf(pj, vv.z, o.z); o.w = fmaf(pj, vv.w, o.w);
     }
-    float* part = r.att_part + ((long long)bh * KS + sl) * (dh + 2);
-    if (lane < dh) part[2 + lane] = o0;
-    if (lane + 32 < dh) part[2 + lane + 32] = o1;
-    if (lane + 64 < dh) part[2 + lane + 64] = o2;
-    if (lane + 96 < dh) part[2 + lane + 96] = o3;
-    if (lane == 0) { part[0] = m; part[1] = l; }
-    // last slice of this (b, head) to finish merges
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) last = atomicAdd(r.att_count + bh, 1) == nsl - 1;
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
+    for (int off = NL; off < 32; off <<= 1) {
+      o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
+      o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
+    }
+    float* pt = r.att_part + ((long long)bh * KS + sl) * PS;
+    if (lane < NL) *reinterpret_cast<float4*>(pt + 4 + lane * 4) = o;
+    if (lane == 0) *reinterpret_cast<float2*>(pt) = make_float2(m, l);
+    if constexpr (MERGE) {
+      // last slice of this (b, head) to finish merges: lane = slice for the weights, lane = (slice group, 4 channels) for o
       __threadfence();
-      const float* pb = r.att_part + (long long)bh * KS * (dh + 2);
-      float M = win == 0 ? 0.f : -INFINITY;               // zero look-back keys of window 0: logit 0 (quirk Q1)
-      for (int k = 0; k < nsl; ++k) M = fmaxf(M, __ldcg(pb + k * (dh + 2)));
-      float Lt = win == 0 ? (float)w * expf(-M) : 0.f;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int k = 0; k < nsl; ++k) {
-        const float* pk = pb + k * (dh + 2);
-        const float f = expf(__ldcg(pk) - M);
-        Lt += __ldcg(pk + 1) * f;
-        if (lane < dh) a0 = fmaf(f, __ldcg(pk + 2 + lane), a0);
-        if (lane + 32 < dh) a1 = fmaf(f, __ldcg(pk + 2 + lane + 32), a1);
-        if (lane + 64 < dh) a2 = fmaf(f, __ldcg(pk + 2 + lane + 64), a2);
-        if (lane + 96 < dh) a3 = fmaf(f, __ldcg(pk + 2 + lane + 96), a3);
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) last = atomicAdd(r.att_count + bh, 1) == nsl - 1;
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        const float* pb = r.att_part + (long long)bh * KS * PS;
+        float4 oreg[NL];
+#pragma unroll
+        for (int jj = 0; jj < NL; ++jj) {
+          const int sx = kg + jj * KG;
+          oreg[jj] = sx < nsl ? __ldcg(reinterpret_cast<const float4*>(pb + sx * PS + 4 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float2 ml = lane < nsl ? __ldcg(reinterpret_cast<const float2*>(pb + lane * PS)) : make_float2(-INFINITY, 0.f);
+        float M = warp_max(ml.x);
+        if (win == 0) M = fmaxf(M, 0.f);                     // zero look-back keys of window 0: logit 0 (quirk Q1)
+        const float f = lane < nsl ? expf(ml.x - M) : 0.f;
+        float Lt = warp_sum(ml.y * f);
+        if (win == 0) Lt += (float)w * expf(-M);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int jj = 0; jj < NL; ++jj) {
+          const int sx = kg + jj * KG;
+          const float fs = __shfl_sync(0xffffffffu, f, sx & 31);               // f = 0 for slices that do not exist
+          a.x = fmaf(fs, oreg[jj].x, a.x); a.y = fmaf(fs, oreg[jj].y, a.y); a.z = fmaf(fs, oreg[jj].z, a.z); a.w = fmaf(fs, oreg[jj].w, a.w);
+        }
+        for (int off = NL; off < 32; off <<= 1) {
+          a.x += __shfl_xor_sync(0xffffffffu, a.x, off); a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+          a.z += __shfl_xor_sync(0xffffffffu, a.z, off); a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+        }
+        const float inv = 1.f / Lt;
+        if (lane < NL) *reinterpret_cast<float4*>(r.att + (long long)b * I + hh * dh + lane * 4) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+        if (lane == 0) r.att_count[bh] = 0;
       }
-      const float inv = 1.f / Lt;
-      float* ao = r.att + (long long)b * I + hh * dh;
-      if (lane < dh) ao[lane] = a0 * inv;
-      if (lane + 32 < dh) ao[lane + 32] = a1 * inv;
-      if (lane + 64 < dh) ao[lane + 64] = a2 * inv;
-      if (lane + 96 < dh) ao[lane + 96] = a3 * inv;
-      if (lane == 0) r.att_count[bh] = 0;
     }
-    __syncwarp();
+  }
+}
+
+template <bool MERGE>
+__device__ void attention_phase(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq) {
+  switch (r.dim_head) {
+    case 64: attention_phase_t<MERGE, 16>(r, kcache, vcache, pos, sq); break;
+    case 32: attention_phase_t<MERGE, 8>(r, kcache, vcache, pos, sq); break;
+    case 16: attention_phase_t<MERGE, 4>(r, kcache, vcache, pos, sq); break;
+    case 8: attention_phase_t<MERGE, 2>(r, kcache, vcache, pos, sq); break;
+    default: attention_phase_t<MERGE, 1>(r, kcache, vcache, pos, sq); break;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ SGU (progen.py:166-184)
 // a = gelu(proj_in) = [xs | gate] (C channels each).  gn = LN(gate) * scale -> history[b][pos]; gate' = sum_{k<=pos} W[pos,k]
-// history[b][k] + bias[pos]; sg = xs * gate'.  Task = (sequence, block of 128 channels); warps split the k range.
-__device__ void sgu_phase(const progen_decode_run_t& r, const progen_decode_layer_t& L, int pos, float* red /* smem [WPB][128] + stats */) {
+// history[b][k] + bias[pos]; sg = xs * gate'.  Task = (sequence, block of 128 channels, split of the history range): the
+// partial gate' goes to sg[split][b][c] (split 0 adds the current position's term and the bias); the SGU projection
+// phase multiplies xs with the sum of the partials while it stages its input (PRO_SGU).
+struct SguArgs { const float* ln_scale; const float* w; const float* b; float* hist; };
+__device__ __forceinline__ int sgu_splits(const progen_decode_run_t& r) {
+  const int base = r.B * (r.hid / 2 / 128);
+  int s = (int)gridDim.x / (base > 0 ? base : 1);
+  return s < 1 ? 1 : (s > MAXSPLIT ? MAXSPLIT : s);
+}
+__device__ void sgu_phase(const progen_decode_run_t& r, const SguArgs& L, int pos, float* red /* smem [WPB][128] + stats */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = r.hid / 2, n = r.n;
   const int cblocks = C / 128;
-  const int tasks = r.B * cblocks;
+  const int S = sgu_splits(r);
+  const int tasks = r.B * cblocks * S;
   float* stat = red + WPB * 128;
   for (int t = blockIdx.x; t < tasks; t += gridDim.x) {
-    const int cb = t % cblocks, b = t / cblocks;
-    const float* gate = r.u + (long long)b * r.hid + C;
-    // LN statistics of the gate row (every task recomputes them: C floats)
-    __syncthreads();
-    {
-      float s = 0.f;
-      for (int c = threadIdx.x; c < C; c += TPB) s += gate[c];
-      s = warp_sum(s);
-      if (lane == 0) red[warp] = s;
-      __syncthreads();
-      if (threadIdx.x == 0) { float tt = 0.f; for (int k = 0; k < WPB; ++k) tt += red[k]; stat[0] = tt / C; }
-      __syncthreads();
-      const float mean = stat[0];
-      float qq = 0.f;
-      for (int c = threadIdx.x; c < C; c += TPB) { const float u = gate[c] - mean; qq += u * u; }
-      qq = warp_sum(qq);
-      if (lane == 0) red[warp] = qq;
-      __syncthreads();
-      if (threadIdx.x == 0) { float tt = 0.f; for (int k = 0; k < WPB; ++k) tt += red[k]; stat[1] = rsqrtf(tt / C + 1e-5f); }
-      __syncthreads();
-    }
-    const float mean = stat[0], rstd = stat[1];
+    const int sp = t % S, cb = (t / S) % cblocks, b = t / (S * cblocks);
     const int c0 = cb * 128 + lane * 4;
-    float4 gnow;
-    {
-      const float4 gv = *reinterpret_cast<const float4*>(gate + c0);
-      const float4 sc = *reinterpret_cast<const float4*>(L.sgu_ln_scale + c0);
+    float* hist = L.hist + (long long)b * n * C;
+    const float* wrow = L.w + (long long)pos * n;
+    const int k_lo = (int)((long long)pos * sp / S), k_hi = (int)((long long)pos * (sp + 1) / S);
+    // history rows of this split, warps interleaved, 8 loads in flight per lane
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kb = k_lo + warp; kb < k_hi; kb += 8 * WPB) {
+      float4 h[8];
+      float wk[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = kb + u * WPB;
+        if (k < k_hi) { wk[u] = __ldg(wrow + k); h[u] = __ldcg(reinterpret_cast<const float4*>(hist + (long long)k * C + c0)); }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (kb + u * WPB < k_hi) {
+          acc.x = fmaf(wk[u], h[u].x, acc.x); acc.y = fmaf(wk[u], h[u].y, acc.y); acc.z = fmaf(wk[u], h[u].z, acc.z); acc.w = fmaf(wk[u], h[u].w, acc.w);
+        }
+      }
+    }
+    float4 gnow = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();                                         // the previous task's readers of red / stat are done
+    if (sp == 0) {
+      // LN of the gate row (C floats): the current position's history row and its own term
+      const float* gate = r.u + (long long)b * r.hid + C;
+      float s = 0.f;
+      for (int c = threadIdx.x * 4; c < C; c += TPB * 4) { const float4 v = __ldcg(reinterpret_cast<const float4*>(gate + c)); s += (v.x + v.y) + (v.z + v.w); }
+      s = warp_sum(s);
+      if (lane == 0) stat[warp] = s;
+      __syncthreads();
+      float tt = 0.f;
+#pragma unroll
+      for (int k = 0; k < WPB; ++k) tt += stat[k];
+      const float mean = tt / C;
+      float qq = 0.f;
+      for (int c = threadIdx.x * 4; c < C; c += TPB * 4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(gate + c));
+        const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+        qq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+      qq = warp_sum(qq);
+      if (lane == 0) stat[WPB + warp] = qq;
+      __syncthreads();
+      tt = 0.f;
+#pragma unroll
+      for (int k = 0; k < WPB; ++k) tt += stat[WPB + k];
+      const float rstd = rsqrtf(tt / C + 1e-5f);
+      const float4 gv = __ldcg(reinterpret_cast<const float4*>(gate + c0));
+      const float4 sc = *reinterpret_cast<const float4*>(L.ln_scale + c0);
       gnow.x = (gv.x - mean) * rstd * sc.x; gnow.y = (gv.y - mean) * rstd * sc.y;
       gnow.z = (gv.z - mean) * rstd * sc.z; gnow.w = (gv.w - mean) * rstd * sc.w;
+      if (warp == 0) *reinterpret_cast<float4*>(hist + (long long)pos * C + c0) = gnow;
     }
-    float* hist = L.gn_hist + (long long)b * n * C;
-    if (warp == 0) *reinterpret_cast<float4*>(hist + (long long)pos * C + c0) = gnow;
-    const float* wrow = L.sgu_w + (long long)pos * n;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = warp; k < pos; k += WPB) {                       // earlier positions from the history
-      const float wk = __ldg(wrow + k);
-      const float4 h = *reinterpret_cast<const float4*>(hist + (long long)k * C + c0);
-      acc.x = fmaf(wk, h.x, acc.x); acc.y = fmaf(wk, h.y, acc.y); acc.z = fmaf(wk, h.z, acc.z); acc.w = fmaf(wk, h.w, acc.w);
-    }
-    __syncthreads();
     *reinterpret_cast<float4*>(red + warp * 128 + lane * 4) = acc;
     __syncthreads();
     if (warp == 0) {
       float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
       for (int k = 0; k < WPB; ++k) {
         const float4 v = *reinterpret_cast<const float4*>(red + k * 128 + lane * 4);
         tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
       }
-      const float wp = __ldg(wrow + pos), bp = L.sgu_b[pos];    // the current position's own term + spatial bias
-      const float4 xv = *reinterpret_cast<const float4*>(r.u + (long long)b * r.hid + c0);
-      float4 o;
-      o.x = xv.x * (fmaf(wp, gnow.x, tot.x) + bp); o.y = xv.y * (fmaf(wp, gnow.y, tot.y) + bp);
-      o.z = xv.z * (fmaf(wp, gnow.z, tot.z) + bp); o.w = xv.w * (fmaf(wp, gnow.w, tot.w) + bp);
-      *reinterpret_cast<float4*>(r.sg + (long long)b * C + c0) = o;
+      if (sp == 0) {
+        const float wp = __ldg(wrow + pos), bp = L.b[pos];    // the current position's own term + spatial bias
+        tot.x = fmaf(wp, gnow.x, tot.x) + bp; tot.y = fmaf(wp, gnow.y, tot.y) + bp;
+        tot.z = fmaf(wp, gnow.z, tot.z) + bp; tot.w = fmaf(wp, gnow.w, tot.w) + bp;
+      }
+      *reinterpret_cast<float4*>(r.sg + ((long long)sp * r.B + b) * C + c0) = tot;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ sampler (one sequence per CTA)
 // utils.py:97-129: top-k filter keeps logits > (k-th largest), the rest become 0.0 and lose their noise; argmax(logits +
-// gumbel) (first maximal index); seq[pos + 1] += index (ADD, quirk Q5).
+// gumbel) (first maximal index); seq[pos + 1] += index (ADD, quirk Q5).  Then the next position's embedding row.
 __device__ void sample_phase(const progen_decode_run_t& r, int pos, float* sv /* smem [V] */, float* red) {
-  const int t = threadIdx.x, V = r.V;
+  const int t = threadIdx.x, V = r.V, lane = t & 31, warp = t >> 5;
+  int* redi = reinterpret_cast<int*>(red + 32);
   for (int b = blockIdx.x; b < r.B; b += gridDim.x) {
     __syncthreads();
     const float* lg = r.logits + (long long)b * V;
-    if (r.logits_all) for (int c = t; c < V; c += TPB) r.logits_all[((long long)b * r.n + pos) * V + c] = lg[c];
-    if (pos + 1 >= r.n || pos + 1 < r.start[b]) continue;                      // the prime is kept; nothing after the end
-    for (int c = t; c < V; c += TPB) sv[c] = lg[c];
-    __syncthreads();
-    float kth = -INFINITY;
-    if (r.top_k > 0) {
+    if (pos + 1 >= r.n) {
+      if (r.logits_all) for (int c = t; c < V; c += TPB) r.logits_all[((long long)b * r.n + pos) * V + c] = __ldcg(lg + c);
+      continue;                                                                // nothing after the end
+    }
+    int tok = r.seq[(long long)b * r.n + pos + 1];
+    const bool draw = pos + 1 >= r.start[b];                                   // (before its start the prime is kept)
+    if (draw || r.logits_all) {
+      for (int c = t; c < V; c += TPB) {
+        const float v = __ldcg(lg + c);
+        sv[c] = v;
+        if (r.logits_all) r.logits_all[((long long)b * r.n + pos) * V + c] = v;
+      }
+    }
+    if (draw) {
+      __syncthreads();
+      float kth = -INFINITY;
+      if (r.top_k > 0) {
+        for (int c = t; c < V; c += TPB) {
+          const float v = sv[c];
+          int gt = 0, ge = 0;
+#pragma unroll 8
+          for (int j = 0; j < V; ++j) { const float u = sv[j]; gt += u > v; ge += u >= v; }
+          if (gt < r.top_k && r.top_k <= ge) red[0] = v;                       // the k-th largest value (with multiplicity)
+        }
+        __syncthreads();
+        kth = red[0];
+      }
+      // first maximal index of (kept logit + noise | 0.0): thread-strided scan, then warp / block arg-max with index ties
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
       for (int c = t; c < V; c += TPB) {
         const float v = sv[c];
-        int gt = 0, ge = 0;
-        for (int j = 0; j < V; ++j) { gt += sv[j] > v; ge += sv[j] >= v; }
-        if (gt < r.top_k && r.top_k <= ge) red[0] = v;                         // the k-th largest value (with multiplicity)
+        const bool keep = r.top_k > 0 ? v > kth : true;
+        const float nz = r.noise ? r.noise[((long long)b * r.n + pos) * V + c] : 0.f;
+        const float x = keep ? v + nz : 0.f;
+        if (x > bv) { bv = x; bi = c; }                                        // ascending c: keeps the first maximum
       }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      __syncthreads();                                                          // red[0] (kth) has been read by everyone
+      if (lane == 0) { red[1 + warp] = bv; redi[warp] = bi; }
       __syncthreads();
-      kth = red[0];
+      float fv = red[1];
+      int fi = redi[0];
+#pragma unroll
+      for (int k = 1; k < WPB; ++k) {
+        const float ov = red[1 + k];
+        const int oi = redi[k];
+        if (ov > fv || (ov == fv && oi < fi)) { fv = ov; fi = oi; }
+      }
+      tok += fi;
+      if (t == 0) r.seq[(long long)b * r.n + pos + 1] = tok;
     }
-    __syncthreads();
-    for (int c = t; c < V; c += TPB) {
-      const float v = sv[c];
-      const bool keep = r.top_k > 0 ? v > kth : true;
-      const float nz = r.noise ? r.noise[((long long)b * r.n + pos) * V + c] : 0.f;
-      sv[c] = keep ? v + nz : 0.f;
-    }
-    __syncthreads();
-    if (t == 0) {
-      int best = 0;
-      float bv = sv[0];
-      for (int j = 1; j < V; ++j) if (sv[j] > bv) { bv = sv[j]; best = j; }
-      r.seq[(long long)b * r.n + pos + 1] += best;
-    }
+    // the next position's embedding row (its token is final now), so the next step starts at layer 0 without a phase
+    const int id = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    for (int c = t * 4; c < r.d; c += TPB * 4)
+      *reinterpret_cast<float4*>(r.x + (long long)b * r.d + c) = *reinterpret_cast<const float4*>(r.embed + (long long)id * r.d + c);
   }
+}
+
+enum { K_NONE = 0, K_GEMV = 1, K_ATT = 2, K_SGU = 3, K_SAMPLE = 4 };
+struct PhaseEnt { int kind, next; Phase ph; };     // next: table index of the following GEMV phase (weights to prefetch)
+__host__ __device__ inline int num_phases(int depth) { return depth * 7 + 2; }
+
+// Phase table (shared memory, built once per launch): per layer QKV | attention | out-proj | FF-in | [SGU | SGU proj] | FF-out,
+// then final LN + head, sampler.  Position-dependent fields (pos) are filled in at use.
+__device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, bool att_consumer_merge, int nsplit) {
+  const int d = r.d, I = r.inner, hid = r.hid;
+  const int nph = num_phases(r.depth);
+  for (int li = threadIdx.x; li < r.depth; li += TPB) {
+    const progen_decode_layer_t L = r.layers[li];
+    PhaseEnt* e = tab + li * 7;
+    for (int j = 0; j < 7; ++j) { e[j].kind = K_NONE; e[j].next = 0; e[j].ph = Phase{}; }
+    Phase ph{};
+    // LN + shift + QKV + rotary + cache
+    ph.wt = L.wqkv_t; ph.bias = nullptr; ph.xin = r.x; ph.ldx = d; ph.out = r.q; ph.ldo = I; ph.N = 3 * I; ph.K = d; ph.epi = EP_ROTARY_CACHE;
+    ph.pro = PRO_LN; ph.ln_scale = L.ln1_scale; ph.ln_prev = r.shift_tokens ? L.shift1 : nullptr;
+    ph.kcache = L.kcache; ph.vcache = L.vcache; ph.inner = I; ph.dim_head = r.dim_head; ph.n = r.n; ph.rot_sin = r.rot_sin; ph.rot_cos = r.rot_cos;
+    e[0].kind = K_GEMV; e[0].ph = ph; e[0].next = li * 7 + 2;
+    ph = Phase{}; ph.kcache = L.kcache; ph.vcache = L.vcache;
+    e[1].kind = K_ATT; e[1].ph = ph;
+    // out-proj + residual
+    ph = Phase{};
+    ph.wt = L.wo_t; ph.bias = L.bo; ph.xin = r.att; ph.ldx = I; ph.out = r.x; ph.ldo = d; ph.N = d; ph.K = I; ph.epi = EP_RESIDUAL;
+    if (att_consumer_merge) { ph.pro = PRO_ATT; ph.aux = r.att_part; ph.window = r.window; ph.dim_head = r.dim_head; }
+    e[2].kind = K_GEMV; e[2].ph = ph; e[2].next = li * 7 + 3;
+    // LN + shift + FF-in (+ GLU / GELU)
+    ph = Phase{};
+    ph.wt = L.win_t; ph.bias = L.bin; ph.xin = r.x; ph.ldx = d; ph.out = r.u; ph.ldo = hid; ph.N = hid; ph.K = d;
+    ph.epi = L.kind == 0 ? EP_GLU : EP_GELU; ph.pro = PRO_LN; ph.ln_scale = L.ln2_scale; ph.ln_prev = r.shift_tokens ? L.shift2 : nullptr;
+    e[3].kind = K_GEMV; e[3].ph = ph; e[3].next = li * 7 + (L.kind == 2 ? 5 : 6);
+    const float* last = r.u;
+    int last_k = hid;
+    if (L.kind == 2) {
+      ph = Phase{}; ph.ln_scale = L.sgu_ln_scale; ph.wt = L.sgu_w; ph.bias = L.sgu_b; ph.kcache = L.gn_hist;
+      e[4].kind = K_SGU; e[4].ph = ph;
+      ph = Phase{};
+      ph.wt = L.sgu_proj_t; ph.bias = L.sgu_proj_b; ph.xin = r.u; ph.ldx = hid; ph.out = r.pj; ph.ldo = hid / 2; ph.N = hid / 2; ph.K = hid / 2;
+      ph.epi = EP_BIAS; ph.pro = PRO_SGU; ph.aux = r.sg; ph.nsplit = nsplit;
+      e[5].kind = K_GEMV; e[5].ph = ph; e[5].next = li * 7 + 6;
+      last = r.pj; last_k = hid / 2;
+    }
+    // FF-out + residual
+    ph = Phase{};
+    ph.wt = L.wout_t; ph.bias = L.bout; ph.xin = last; ph.ldx = last_k; ph.out = r.x; ph.ldo = d; ph.N = d; ph.K = last_k; ph.epi = EP_RESIDUAL;
+    e[6].kind = K_GEMV; e[6].ph = ph; e[6].next = li + 1 < r.depth ? (li + 1) * 7 : nph - 2;
+  }
+  if (threadIdx.x == 0) {
+    // final LN + logits (progen.py:219-222), then the sampler
+    Phase ph{};
+    ph.wt = r.whead_t; ph.bias = r.bhead; ph.xin = r.x; ph.ldx = d; ph.out = r.logits; ph.ldo = r.V; ph.N = r.V; ph.K = d; ph.epi = EP_BIAS;
+    ph.pro = PRO_LN; ph.ln_scale = r.lnf_scale; ph.ln_prev = nullptr;
+    tab[nph - 2].kind = K_GEMV; tab[nph - 2].ph = ph; tab[nph - 2].next = 0;
+    tab[nph - 1].kind = K_SAMPLE; tab[nph - 1].next = 0; tab[nph - 1].ph = Phase{};
+  }
+  __syncthreads();
+}
+
+template <int BT> constexpr size_t decode_smem_floats() {
+  return (size_t)BT * Tile<BT>::XP + Tile<BT>::PART + Tile<BT>::STATF + Tile<BT>::WSM + WPB * 128 + 64;
 }
 
 template <int BT, typename TW>
 __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_decode_run_t r) {
-  extern __shared__ float smem[];
-  float* xs = smem;                                    // [BT][KC]
-  float* red = smem + BT * KC;                         // scratch: WPB*128 + 2*BT + 16
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                                    // [BT][XP]
+  float* part = xs + BT * Tile<BT>::XP;                // partial sums
+  float* stat = part + Tile<BT>::PART;                 // [STATF]
+  float* wsm = stat + Tile<BT>::STATF;                 // lane = sequence: fp32 weights of one wave
+  float* red = wsm + Tile<BT>::WSM;                    // scratch of the other phases: WPB * 128 + 64
+  PhaseEnt* tab = reinterpret_cast<PhaseEnt*>(red + WPB * 128 + 64);
+  const int nph = num_phases(r.depth);
+  constexpr bool MERGE_IN_ATT = BT > 1;
+  const bool att_consumer = !MERGE_IN_ATT && r.inner <= 4 * TPB;
+  build_phase_table(r, tab, att_consumer, sgu_splits(r));
+  for (int i = threadIdx.x; i < BT * Tile<BT>::XP; i += TPB) xs[i] = 0.f;     // tails beyond K are multiplied by zero weights: keep them finite
+  __syncthreads();
   unsigned int round = 0;
-  const int d = r.d, I = r.inner, hid = r.hid, B = r.B;
+  const int d = r.d, B = r.B;
+  Prof pf{r.prof, 0, false};
+  WRegs<TW> w;
+  Pre pre{};
+  bool have = false;                                   // `w`, `pre` hold the next GEMV phase's prefetch
   for (int step = 0; step < r.nsteps; ++step) {
     const int pos = r.pos0 + step;
-    // ---- embedding: x[b] = embed[clamp(seq[b][pos])]
-    for (int idx = blockIdx.x * TPB + threadIdx.x; idx < B * (d >> 2); idx += gridDim.x * TPB) {
-      const int b = idx / (d >> 2), c = (idx % (d >> 2)) * 4;
-      int id = r.seq[(long long)b * r.n + pos];
-      id = id < 0 ? 0 : (id >= r.V ? r.V - 1 : id);
-      *reinterpret_cast<float4*>(r.x + (long long)b * d + c) = *reinterpret_cast<const float4*>(r.embed + (long long)id * d + c);
-    }
-    grid_sync(r.grid_bar, round);
-    for (int li = 0; li < r.depth; ++li) {
-      const progen_decode_layer_t& L = r.layers[li];
-      Phase ph{};
-      // ---- LN + shift + QKV + rotary + cache
-      ph.wt = L.wqkv_t; ph.bias = nullptr; ph.xin = r.x; ph.ldx = d; ph.out = r.q; ph.ldo = I; ph.N = 3 * I; ph.K = d; ph.epi = EP_ROTARY_CACHE;
-      ph.pro = PRO_LN; ph.ln_scale = L.ln1_scale; ph.ln_prev = r.shift_tokens ? L.shift1 : nullptr;
-      ph.kcache = L.kcache; ph.vcache = L.vcache; ph.inner = I; ph.dim_head = r.dim_head; ph.n = r.n; ph.rot_sin = r.rot_sin; ph.rot_cos = r.rot_cos; ph.pos = pos;
-      gemv_phase<BT, TW>(ph, B, xs, red);
-      grid_sync(r.grid_bar, round);
-      attention_phase(r, L, pos, red);
-      grid_sync(r.grid_bar, round);
-      // ---- out-proj + residual
-      ph = Phase{};
-      ph.wt = L.wo_t; ph.bias = L.bo; ph.xin = r.att; ph.ldx = I; ph.out = r.x; ph.ldo = d; ph.N = d; ph.K = I; ph.epi = EP_RESIDUAL; ph.pos = pos;
-      gemv_phase<BT, TW>(ph, B, xs, red);
-      grid_sync(r.grid_bar, round);
-      // ---- LN + shift + FF-in (+ GLU / GELU)
-      ph = Phase{};
-      ph.wt = L.win_t; ph.bias = L.bin; ph.xin = r.x; ph.ldx = d; ph.out = r.u; ph.ldo = hid; ph.N = hid; ph.K = d;
-      ph.epi = L.kind == 0 ? EP_GLU : EP_GELU; ph.pro = PRO_LN; ph.ln_scale = L.ln2_scale; ph.ln_prev = r.shift_tokens ? L.shift2 : nullptr; ph.pos = pos;
-      gemv_phase<BT, TW>(ph, B, xs, red);
-      grid_sync(r.grid_bar, round);
-      const float* last = r.u;
-      int last_k = hid, last_ld = hid;
-      if (L.kind == 2) {
-        sgu_phase(r, L, pos, red);
-        grid_sync(r.grid_bar, round);
-        ph = Phase{};
-        ph.wt = L.sgu_proj_t; ph.bias = L.sgu_proj_b; ph.xin = r.sg; ph.ldx = hid / 2; ph.out = r.pj; ph.ldo = hid / 2; ph.N = hid / 2; ph.K = hid / 2;
-        ph.epi = EP_BIAS; ph.pos = pos;
-        gemv_phase<BT, TW>(ph, B, xs, red);
-        grid_sync(r.grid_bar, round);
-        last = r.pj; last_k = hid / 2; last_ld = hid / 2;
+    pf.on = r.prof != nullptr && step == r.nsteps - 1 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+    pf.ev = 0;
+    if (step == 0) {
+      // embedding of the launch's first position (later ones are written by the sampler phase)
+      for (int idx = blockIdx.x * TPB + threadIdx.x; idx < B * (d >> 2); idx += gridDim.x * TPB) {
+        const int b = idx / (d >> 2), c = (idx % (d >> 2)) * 4;
+        int id = r.seq[(long long)b * r.n + pos];
+        id = id < 0 ? 0 : (id >= r.V ? r.V - 1 : id);
+        *reinterpret_cast<float4*>(r.x + (long long)b * d + c) = *reinterpret_cast<const float4*>(r.embed + (long long)id * d + c);
       }
-      // ---- FF-out + residual
-      ph = Phase{};
-      ph.wt = L.wout_t; ph.bias = L.bout; ph.xin = last; ph.ldx = last_ld; ph.out = r.x; ph.ldo = d; ph.N = d; ph.K = last_k; ph.epi = EP_RESIDUAL; ph.pos = pos;
-      gemv_phase<BT, TW>(ph, B, xs, red);
-      grid_sync(r.grid_bar, round);
+      grid_sync(r.grid_bar, round, pf);
     }
-    // ---- final LN + logits (progen.py:219-222), then the sampler
-    Phase ph{};
-    ph.wt = r.whead_t; ph.bias = r.bhead; ph.xin = r.x; ph.ldx = d; ph.out = r.logits; ph.ldo = r.V; ph.N = r.V; ph.K = d; ph.epi = EP_BIAS;
-    ph.pro = PRO_LN; ph.ln_scale = r.lnf_scale; ph.ln_prev = nullptr; ph.pos = pos;
-    gemv_phase<BT, TW>(ph, B, xs, red);
-    grid_sync(r.grid_bar, round);
-    sample_phase(r, pos, xs, red);
-    grid_sync(r.grid_bar, round);
+    for (int e = 0; e < nph; ++e) {
+      const int kind = tab[e].kind;
+      if (kind == K_NONE) continue;
+      if (kind == K_GEMV) {
+        Phase ph = tab[e].ph;
+        ph.pos = pos;
+        if (!have) prefetch_phase<BT, TW>(ph, w, pre);
+        prof_mark(pf, 0);
+        gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf);
+        prof_mark(pf, 3);
+        have = !(e == nph - 2 && step + 1 == r.nsteps);
+        if (have) {
+          Phase nx = tab[tab[e].next].ph;
+          nx.pos = e == nph - 2 ? pos + 1 : pos;               // the head's successor is layer 0 of the next position
+          prefetch_phase<BT, TW>(nx, w, pre);
+        }
+        prof_mark(pf, 4);
+      } else if (kind == K_ATT) {
+        if (MERGE_IN_ATT || !att_consumer) attention_phase<true>(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
+        else attention_phase<false>(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
+      } else if (kind == K_SGU) {
+        const SguArgs sa{tab[e].ph.ln_scale, reinterpret_cast<const float*>(tab[e].ph.wt), tab[e].ph.bias, tab[e].ph.kcache};
+        sgu_phase(r, sa, pos, red);
+      } else {
+        sample_phase(r, pos, xs, red);
+      }
+      grid_sync(r.grid_bar, round, pf);
+    }
   }
 }
 
 template <int BT, typename TW>
 int launch_run(const progen_decode_run_t& r, cudaStream_t s) {
-  const size_t smem = (size_t)(BT * KC + WPB * 128 + 2 * BT + 64) * sizeof(float);
+  static_assert((BT * Tile<BT>::XP) % 4 == 0 && Tile<BT>::PART % 4 == 0 && Tile<BT>::WSM % 4 == 0, "the scratch regions must stay 16-byte aligned");
+  const size_t smem = decode_smem_floats<BT>() * sizeof(float) + (size_t)num_phases(r.depth) * sizeof(PhaseEnt);
+  PG_CHECK_ARG(smem <= 227 * 1024);
   auto kern = decode_persistent_kernel<BT, TW>;
-  static bool once = false;
-  if (!once) {
+  static size_t set_for = 0;
+  if (set_for < smem) {
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    once = true;
+    set_for = smem;
   }
   int per_sm = 0;
   PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
@@ -494,8 +1011,11 @@ extern "C" {
 // (the kernel leaves att_count zero; the caller re-zeroes grid_bar before the next launch).
 int progen_decode_run(const progen_decode_run_t* r, void* stream) {
   PG_CHECK_ARG(r != nullptr && r->layers != nullptr && r->depth > 0 && r->B >= 1 && r->B <= 64 && r->nsteps >= 0);
-  PG_CHECK_ARG(r->d % 8 == 0 && r->inner % 8 == 0 && r->hid % 256 == 0 && r->V % 2 == 0 && r->V <= KC);
-  PG_CHECK_ARG(r->dim_head % 4 == 0 && r->dim_head <= 128 && r->pos0 >= 0 && r->pos0 + r->nsteps <= r->n);
+  PG_CHECK_ARG(r->d % 8 == 0 && r->inner % 8 == 0 && r->hid % 256 == 0 && r->V % 2 == 0 && r->V <= 512);
+  PG_CHECK_ARG(r->d <= 8192 && r->inner <= 8192 && r->hid <= 8192);   // K segments of one pair fit a wave (KS <= WSEGS)
+  PG_CHECK_ARG(r->dim_head >= 4 && r->dim_head <= 64 && (r->dim_head & (r->dim_head - 1)) == 0);   // float4 lanes per value row
+  PG_CHECK_ARG(r->window >= 1 && r->window <= 512);                    // <= 32 key slices per (sequence, head)
+  PG_CHECK_ARG(r->pos0 >= 0 && r->pos0 + r->nsteps <= r->n);
   PG_CHECK_ARG(r->grid_bar != nullptr && r->att_count != nullptr && r->att_part != nullptr);
   if (r->nsteps == 0) return PROGEN_OK;
   cudaStream_t s = (cudaStream_t)stream;

@@ -76,75 +76,76 @@ template <typename T> __device__ __forceinline__ void st4(uint8_t* p, const floa
 }
 
 // TI: dtype of x; TO: dtype of dy / dout; NCH: ceil(d / 128) upper bound (accumulator registers)
-template <typename TI, typename TO, int NCH, bool RESIDUAL>
-__global__ void __launch_bounds__(THREADS, 1) ln_shift_bwd_stream_kernel(const LnStreamArgs a) {
+template <typename TI, typename TO, int NCH, bool RESIDUAL, int RBT>
+__global__ void __launch_bounds__(32 * (RBT * CG + 1), 1) ln_shift_bwd_stream_kernel(const LnStreamArgs a) {
+  constexpr int CWT = RBT * CG;               // consumer warps (RBT rows per stage: 8, or 4 for rows wider than 1024 so that >= 2 stages fit)
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES];
-  __shared__ float red[CW][128];
+  __shared__ float red[CWT][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d, half = d >> 1;
   const uint32_t smem0 = smem_u32(smem);
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto done_bar = [&](int s) { return smem_u32(&bars[MAX_STAGES + s]); };
-  const long long nchunks = a.T / RB;
+  const long long nchunks = a.T / RBT;
   const long long n_my = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const bool has_out = a.dout != nullptr;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(done_bar(s), RB); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(done_bar(s), RBT); }
     fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp == CW) {
+  if (warp == CWT) {
     // ============================================================ producer: bulk loads in, bulk stores out
     const uint32_t xrow = d * (uint32_t)sizeof(TI), yrow = d * (uint32_t)sizeof(TO), rrow = d * 4u;
-    const int dy_rows = a.shift ? RB + 1 : RB;
+    const int dy_rows = a.shift ? RBT + 1 : RBT;
     const bool x_contig = a.ldx == d, dy_contig = a.lddy == d;
-    uint32_t tx = RB * xrow + 2 * RB * 4u + (RESIDUAL ? RB * rrow : 0u);
+    uint32_t tx = RBT * xrow + 2 * RBT * 4u + (RESIDUAL ? RBT * rrow : 0u);
     for (long long it = 0; it < n_my + a.stages; ++it) {
       const int stage = (int)(it % a.stages);
       const uint32_t sbase = smem0 + stage * a.stage_bytes;
       if (it >= a.stages) {
         // the chunk that used this stage: wait for the 8 consumer warps, store its results, wait until smem is read
-        const long long t0 = (blockIdx.x + (it - a.stages) * gridDim.x) * RB;
+        const long long t0 = (blockIdx.x + (it - a.stages) * gridDim.x) * RBT;
         mbar_wait(done_bar(stage), (uint32_t)((it / a.stages) - 1) & 1u);
         // one bulk copy per ARRAY when its rows are contiguous (the TMA unit costs ~100 cycles per request, so 1-2 KB
         // row-sized requests cap a d = 512 stream near 4 TB/s), one per row otherwise (column slices of wider buffers)
-        if (lane <= RB) {
+        if (lane <= RBT) {
           bool issued = false;
-          if (lane == RB) {
-            if constexpr (RESIDUAL) { bulk_store(a.dres + t0 * (long long)d, sbase + a.off_r, RB * rrow); issued = true; }
+          if (lane == RBT) {
+            if constexpr (RESIDUAL) { bulk_store(a.dres + t0 * (long long)d, sbase + a.off_r, RBT * rrow); issued = true; }
           }
           if (issued) { bulk_commit(); bulk_wait_read(); }
         }
         __syncwarp();
       }
       if (it < n_my) {
-        const long long t0 = (blockIdx.x + it * gridDim.x) * RB;
-        const int ny = (t0 + dy_rows <= a.T) ? dy_rows : RB;           // the look-ahead row does not exist after the last row
+        const long long t0 = (blockIdx.x + it * gridDim.x) * RBT;
+        const int ny = (t0 + dy_rows <= a.T) ? dy_rows : RBT;           // the look-ahead row does not exist after the last row
         if (lane == 0) mbar_expect_tx(full_bar(stage), tx + ny * yrow);
         __syncwarp();
         const uint32_t fb = full_bar(stage);
-        if (lane < RB) {
+        if (lane < RBT) {
           const TI* xs = reinterpret_cast<const TI*>(a.x) + (t0 + lane) * a.ldx;
           if (!x_contig) bulk_load(sbase + lane * xrow, xs, xrow, fb);
-          else if (lane == 0) bulk_load(sbase, xs, RB * xrow, fb);
-        } else if (lane < RB + 9) {
-          const int r = lane - RB;
+          else if (lane == 0) bulk_load(sbase, xs, RBT * xrow, fb);
+        } else if (lane < RBT + 9) {
+          const int r = lane - RBT;
           const TO* ys = reinterpret_cast<const TO*>(a.dy) + (t0 + r) * a.lddy;
           if (!dy_contig) { if (r < ny) bulk_load(sbase + a.off_dy + r * yrow, ys, yrow, fb); }
           else if (r == 0) bulk_load(sbase + a.off_dy, ys, ny * yrow, fb);
-        } else if (lane == RB + 9) {
-          bulk_load(sbase + a.off_stat, a.mean + t0, RB * 4u, fb);
-        } else if (lane == RB + 10) {
-          bulk_load(sbase + a.off_stat + RB * 4u, a.rstd + t0, RB * 4u, fb);
-        } else if (lane == RB + 11) {
-          if constexpr (RESIDUAL) bulk_load(sbase + a.off_r, a.dres + t0 * (long long)d, RB * rrow, fb);
+        } else if (lane == RBT + 9) {
+          bulk_load(sbase + a.off_stat, a.mean + t0, RBT * 4u, fb);
+        } else if (lane == RBT + 10) {
+          bulk_load(sbase + a.off_stat + RBT * 4u, a.rstd + t0, RBT * 4u, fb);
+        } else if (lane == RBT + 11) {
+          if constexpr (RESIDUAL) bulk_load(sbase + a.off_r, a.dres + t0 * (long long)d, RBT * rrow, fb);
         }
       }
     }
-    if (lane <= RB) bulk_wait_all();
+    if (lane <= RBT) bulk_wait_all();
     return;
   }
 
@@ -170,16 +171,16 @@ __global__ void __launch_bounds__(THREADS, 1) ln_shift_bwd_stream_kernel(const L
       s4[0] = t.x; s4[1] = t.y; s4[2] = t.z; s4[3] = t.w;
     }
   };
-  const int group = warp / RB, row = warp % RB;
+  const int group = warp / RBT, row = warp % RBT;
   constexpr bool KEEP = NCH <= 4;             // the row's xhat / g*scale stay in registers between the two passes
   for (long long it = group; it < n_my; it += CG) {
     const int stage = (int)(it % a.stages);
     uint8_t* sb = smem + stage * a.stage_bytes;
-    const long long t = (blockIdx.x + it * gridDim.x) * RB + row;
+    const long long t = (blockIdx.x + it * gridDim.x) * RBT + row;
     const bool has_next = (int)(t % a.seq_len) + 1 < a.seq_len;
     mbar_wait(full_bar(stage), (uint32_t)(it / a.stages) & 1u);
     const float mean = reinterpret_cast<const float*>(sb + a.off_stat)[row];
-    const float rstd = reinterpret_cast<const float*>(sb + a.off_stat)[RB + row];
+    const float rstd = reinterpret_cast<const float*>(sb + a.off_stat)[RBT + row];
     const uint8_t* xr = sb + (size_t)row * d * sizeof(TI);
     const uint8_t* yr = sb + a.off_dy + (size_t)row * d * sizeof(TO);
     const uint8_t* yn = yr + (size_t)d * sizeof(TO);
@@ -259,31 +260,35 @@ __global__ void __launch_bounds__(THREADS, 1) ln_shift_bwd_stream_kernel(const L
       if (dst == nullptr) continue;            // CTA-uniform
 #pragma unroll
       for (int i = 0; i < 4; ++i) red[warp][lane * 4 + i] = pass == 0 ? ds_acc[ch][i] : cs_acc[RESIDUAL ? ch : 0][i];
-      named_bar_sync(1, 32 * CW);
+      named_bar_sync(1, 32 * CWT);
       if (threadIdx.x < 128) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < CW; ++w) s += red[w][threadIdx.x];
+        for (int w = 0; w < CWT; ++w) s += red[w][threadIdx.x];
         const int c = ch * 128 + threadIdx.x;
         if (c < d) atomicAdd(dst + c, s);
       }
-      named_bar_sync(1, 32 * CW);
+      named_bar_sync(1, 32 * CWT);
     }
   }
 }
 
 template <typename TI, typename TO, bool RESIDUAL>
-int launch_stream(const LnStreamArgs& a, int smem_bytes, cudaStream_t s) {
-  const long long nchunks = a.T / RB;
+int launch_stream(const LnStreamArgs& a, int smem_bytes, int rbt, cudaStream_t s) {
+  const long long nchunks = a.T / rbt;
   const int grid = (int)(nchunks < pg_num_sms() ? nchunks : pg_num_sms());
-  static bool attr_set = false;               // per (TI, TO, RESIDUAL): both NCH variants get the full opt-in once
+  static bool attr_set = false;               // per (TI, TO, RESIDUAL): every variant gets the full opt-in once
   if (!attr_set) {
-    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 4, RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 8, RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 4, RESIDUAL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 8, RESIDUAL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 12, RESIDUAL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    PG_CUDA(cudaFuncSetAttribute(ln_shift_bwd_stream_kernel<TI, TO, 16, RESIDUAL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;
   }
-  if (a.d <= 512) ln_shift_bwd_stream_kernel<TI, TO, 4, RESIDUAL><<<grid, THREADS, smem_bytes, s>>>(a);
-  else ln_shift_bwd_stream_kernel<TI, TO, 8, RESIDUAL><<<grid, THREADS, smem_bytes, s>>>(a);
+  if (a.d <= 512) ln_shift_bwd_stream_kernel<TI, TO, 4, RESIDUAL, 8><<<grid, 32 * (8 * CG + 1), smem_bytes, s>>>(a);
+  else if (a.d <= 1024) ln_shift_bwd_stream_kernel<TI, TO, 8, RESIDUAL, 8><<<grid, 32 * (8 * CG + 1), smem_bytes, s>>>(a);
+  else if (a.d <= 1536) ln_shift_bwd_stream_kernel<TI, TO, 12, RESIDUAL, 4><<<grid, 32 * (4 * CG + 1), smem_bytes, s>>>(a);
+  else ln_shift_bwd_stream_kernel<TI, TO, 16, RESIDUAL, 4><<<grid, 32 * (4 * CG + 1), smem_bytes, s>>>(a);
   PG_LAUNCH_CHECK();
   return PROGEN_OK;
 }
@@ -298,7 +303,8 @@ int ln_shift_bwd_stream_launch(const void* dy, long long lddy, int act_dtype, co
   static int enabled = [] { const char* e = getenv("PROGEN_LN_STREAM"); return e ? atoi(e) : 1; }();
   if (!enabled) return 1;
   const int so = act_dtype == PG_BF16 ? 2 : 4, si = x_dtype == PG_BF16 ? 2 : 4;
-  if (T % RB != 0 || T % seq_len != 0 || d % 128 != 0 || d > 1024 || T < 8 * RB) return 1;
+  const int rbt = d > 1024 ? 4 : RB;             // rows per stage: wide rows (config 4: d = 1536, gMLP 2d = 2048) take 4 so that >= 3 stages fit
+  if (T % RB != 0 || T % seq_len != 0 || d % 128 != 0 || d > 2048 || T < 8 * RB) return 1;
   // every bulk copy: 16-byte aligned addresses and sizes
   if ((lddy * so) % 16 || (ldx * si) % 16 || (ldo * so) % 16) return 1;
   if (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dout | (uintptr_t)dres | (uintptr_t)mean | (uintptr_t)rstd) % 16) return 1;
@@ -307,9 +313,9 @@ int ln_shift_bwd_stream_launch(const void* dy, long long lddy, int act_dtype, co
   a.dout = dout; a.ldo = ldo; a.dscale = dscale; a.dres_colsum = residual ? dres_colsum : nullptr;
   a.T = T; a.d = d; a.seq_len = seq_len; a.shift = shift;
   auto up = [](int v) { return (v + 127) & ~127; };
-  int off = up(RB * d * si);
-  a.off_dy = off; off += up((RB + 1) * d * so);
-  a.off_r = off; if (residual) off += up(RB * d * 4);
+  int off = up(rbt * d * si);
+  a.off_dy = off; off += up((rbt + 1) * d * so);
+  a.off_r = off; if (residual) off += up(rbt * d * 4);
   a.off_out = off;                               // (no longer staged: written directly)
   a.off_stat = off; off += 128;
   a.stage_bytes = off;
@@ -317,7 +323,7 @@ int ln_shift_bwd_stream_launch(const void* dy, long long lddy, int act_dtype, co
   if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
   if (a.stages < 2) return 1;
   const int smem_bytes = a.stages * a.stage_bytes;
-#define LNS(TI, TO, RES) return launch_stream<TI, TO, RES>(a, smem_bytes, stream)
+#define LNS(TI, TO, RES) return launch_stream<TI, TO, RES>(a, smem_bytes, rbt, stream)
   if (residual) {
     if (x_dtype != PG_F32) return 1;
     if (act_dtype == PG_F32) LNS(float, float, true);

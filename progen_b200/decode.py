@@ -33,7 +33,7 @@ class DecodeRun(C.Structure):
     _fields_ = [(k, _I) for k in ('n', 'd', 'heads', 'dim_head', 'inner', 'window', 'hid', 'V', 'depth', 'wdtype', 'shift_tokens',
                                   'top_k', 'B', 'pos0', 'nsteps', '_pad')] + \
                [(k, _P) for k in ('embed', 'lnf_scale', 'whead_t', 'bhead', 'rot_sin', 'rot_cos', 'layers', 'seq', 'start', 'noise',
-                                  'logits_all', 'x', 'q', 'att', 'att_part', 'att_count', 'u', 'sg', 'pj', 'logits', 'grid_bar')]
+                                  'logits_all', 'x', 'q', 'att', 'att_part', 'att_count', 'u', 'sg', 'pj', 'logits', 'grid_bar', 'prof')]
 
 
 class BatchDecoder:
@@ -113,10 +113,10 @@ class BatchDecoder:
         m.noise = 0
         ks = (2 * cfg['window_size'] + 31) // 32
         m.x, m.q, m.att = zeros(B, d), zeros(B, I), zeros(B, I)
-        m.att_part = zeros(B, cfg['heads'], ks, cfg['dim_head'] + 2)
+        m.att_part = zeros(B, cfg['heads'], ks, cfg['dim_head'] + 4)
         self.att_count = torch.zeros(B * cfg['heads'], device=self.dev, dtype=torch.int32)
         m.att_count = self.att_count.data_ptr()
-        m.u, m.sg, m.pj, m.logits = zeros(B, hid), zeros(B, hid // 2), zeros(B, hid // 2), zeros(B, self.V)
+        m.u, m.sg, m.pj, m.logits = zeros(B, hid), zeros(8, B, hid // 2), zeros(B, hid // 2), zeros(B, self.V)
         self.grid_bar = torch.zeros(1, device=self.dev, dtype=torch.int32)
         m.grid_bar = self.grid_bar.data_ptr()
 
@@ -132,6 +132,22 @@ class BatchDecoder:
         for t in self.state:
             t.zero_()
         self.att_count.zero_()
+
+    def profile_barriers(self, pos0, nsteps):
+        """Run, recording clock64 at entry / exit of every grid barrier of the LAST step on CTA 0 and the last CTA.
+        Returns an int64 array [2, events, 2] (events = barriers of one step)."""
+        prof = torch.zeros(2 * 160 * 2 + 160 * 8, device=self.dev, dtype=torch.int64)
+        self.m.prof = prof.data_ptr()
+        try:
+            self.run(pos0, nsteps)
+            torch.cuda.synchronize()
+        finally:
+            self.m.prof = 0
+        raw = prof.cpu().numpy()
+        p = raw[:640].reshape(2, 160, 2)
+        ev = int((p[0, :, 0] != 0).sum())
+        self.last_marks = raw[640:].reshape(160, 8)[:ev]      # clock64 inside CTA 0's phases (0 = not recorded)
+        return p[:, :ev]
 
     def run(self, pos0, nsteps):
         self.grid_bar.zero_()

@@ -99,7 +99,7 @@ def test_ln_strided_act_input():
 
 
 @pytest.mark.parametrize('act', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('d,B,n', [(512, 8, 1024), (1024, 5, 768), (128, 16, 64)])
+@pytest.mark.parametrize('d,B,n', [(512, 8, 1024), (1024, 5, 768), (128, 16, 64), (1536, 4, 768), (2048, 3, 516)])
 def test_ln_bwd_stream_path_residual(act, d, B, n):
     """Shapes the bulk-copy streaming kernel (ln_stream.cu) takes: many chunks per CTA so every stage wraps several
     times, sequence boundaries inside chunks' look-ahead rows, residual accumulate + low-precision copy + column sums."""
