@@ -48,14 +48,17 @@ struct Prof { long long* buf; int ev; bool on; };
 __device__ __forceinline__ void prof_mark(const Prof& pf, int k) {
   if (pf.on && blockIdx.x == 0 && threadIdx.x == 0 && pf.ev < MAXEV) pf.buf[4 * MAXEV + pf.ev * 8 + k] = clock64();
 }
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round, Prof& pf) {
+__device__ __forceinline__ void grid_arrive(unsigned int* bar, unsigned int& round, Prof& pf, long long& t0) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    long long t0 = 0;
     if (pf.on) t0 = clock64();
     ++round;
     __threadfence();
     atomicAdd(bar, 1u);
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int round, Prof& pf, long long t0) {
+  if (threadIdx.x == 0) {
     const unsigned int target = round * gridDim.x;
     unsigned int v;
     do {
@@ -68,6 +71,11 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round
     }
   }
   __syncthreads();
+}
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round, Prof& pf) {
+  long long t0 = 0;
+  grid_arrive(bar, round, pf, t0);
+  grid_wait(bar, round, pf, t0);
 }
 
 // 8 consecutive weights of a row as one lane's registers: bf16 = one 16-byte load, fp32 = two
@@ -89,11 +97,14 @@ __device__ __forceinline__ void w8_unpack(const W8<float>& w, float (&f)[8]) {
   f[0] = __uint_as_float(w.q[0].x); f[1] = __uint_as_float(w.q[0].y); f[2] = __uint_as_float(w.q[0].z); f[3] = __uint_as_float(w.q[0].w);
   f[4] = __uint_as_float(w.q[1].x); f[5] = __uint_as_float(w.q[1].y); f[6] = __uint_as_float(w.q[1].z); f[7] = __uint_as_float(w.q[1].w);
 }
-template <typename TW> struct WRegs { W8<TW> a[MAXSEG], c[MAXSEG]; };
+template <typename TW> struct WRegs { W8<TW> a[MAXSEG], c[MAXSEG]; int pl[MAXSEG], ks[MAXSEG]; };   // + each unit's (pair, K segment) in its wave
 
 enum { EP_BIAS = 0, EP_ROTARY_CACHE = 1, EP_RESIDUAL = 2, EP_GLU = 3, EP_GELU = 4 };
 enum { PRO_NONE = 0, PRO_LN = 1, PRO_ATT = 2, PRO_SGU = 3 };
 
+// CTA c owns the output row PAIRS [c*P/G, (c+1)*P/G) of a GEMV phase, cut along K into 256-column segments; a wave is PW pairs
+// x KS segments <= WSEGS slots, slot s -> warp s % WPB, unit s / WPB of that warp
+struct Geo { int p_lo, np, KS, PW, nwaves; };
 struct Phase {
   const void* wt;          // [N(,x2 for GLU), K]
   const float* bias;       // [N] or null
@@ -114,19 +125,19 @@ struct Phase {
   float* kcache; float* vcache; int inner, dim_head, n;
   const float* rot_sin; const float* rot_cos;
   int pos;
+  Geo g;                   // this CTA's share (filled when the table is built)
 };
 
 // values a thread needs in a phase that do NOT depend on the previous phase: loaded before the barrier (BT == 1 only)
-struct Pre { float b0, b1, o0, o1, sn, cs; float4 sc, pv; };
+struct Pre { float b0, b1, o0, o1, sn, cs; float4 sc, pv; float* d0; float* d1; };   // d0 / d1: where the pair's two results go
 
 // Work split of one GEMV phase: CTA c owns the output row PAIRS [c*P/G, (c+1)*P/G) (pair = rows 2p, 2p+1, or p, p+N for
 // GLU), cut along K into 256-column segments; a wave is PW pairs x KS segments <= WSEGS slots, slot s -> warp s % WPB.
-struct Geo { int p_lo, np, KS, PW, nwaves; };
-__device__ __forceinline__ Geo phase_geo(const Phase& ph) {
+__device__ __forceinline__ Geo make_geo(const Phase& ph) {
   const int npairs = ph.epi == EP_GLU ? ph.N : ph.N >> 1;
   Geo g;
-  g.p_lo = (int)((long long)blockIdx.x * npairs / gridDim.x);
-  g.np = (int)((long long)(blockIdx.x + 1) * npairs / gridDim.x) - g.p_lo;
+  g.p_lo = (int)(blockIdx.x * (unsigned)npairs / gridDim.x);              // npairs <= 8192, grid <= a few hundred: 32 bits
+  g.np = (int)((blockIdx.x + 1) * (unsigned)npairs / gridDim.x) - g.p_lo;
   g.KS = (ph.K + 255) >> 8;
   g.PW = WSEGS / g.KS;
   g.nwaves = (g.np + g.PW - 1) / g.PW;
@@ -146,6 +157,7 @@ __device__ __forceinline__ void load_wave(const Phase& ph, const Geo& g, int wav
     const int sw = warp + WPB * i;
     const int pl = sw / g.KS, ks = sw - pl * g.KS;
     const int k = ks * 256 + lane * 8;
+    w.pl[i] = pl; w.ks[i] = ks;
     if (pl < pw && k < ph.K) {
       const int pair = g.p_lo + pbase + pl;
       const long long r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
@@ -161,7 +173,7 @@ __device__ __forceinline__ void load_wave(const Phase& ph, const Geo& g, int wav
 // everything of phase `ph` (pos filled in) that can be loaded before the barrier in front of it
 template <int BT, typename TW>
 __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pre& pre) {
-  const Geo g = phase_geo(ph);
+  const Geo& g = ph.g;
   load_wave<TW>(ph, g, 0, w);
   if constexpr (BT == 1) {
     const int t = threadIdx.x;
@@ -170,10 +182,14 @@ __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pr
       const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
       pre.b0 = ph.bias ? ph.bias[r0] : 0.f;
       pre.b1 = ph.bias ? ph.bias[r1] : 0.f;
+      pre.d0 = ph.out + r0; pre.d1 = ph.out + r1;
       if (ph.epi == EP_RESIDUAL) { pre.o0 = __ldcg(ph.out + r0); pre.o1 = __ldcg(ph.out + r1); }
       if (ph.epi == EP_ROTARY_CACHE) {
         const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
         pre.sn = ph.rot_sin[ph.pos * hd + j]; pre.cs = ph.rot_cos[ph.pos * hd + j];
+        const int sec = r0 / ph.inner, c = r0 % ph.inner;
+        pre.d0 = sec == 0 ? ph.out + c : (sec == 1 ? ph.kcache : ph.vcache) + (long long)ph.pos * ph.inner + c;
+        pre.d1 = pre.d0 + 1;
       }
     }
     const int k = t * 4;
@@ -249,7 +265,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
   constexpr int KCB = Tile<BT>::KCB, XP = Tile<BT>::XP, BTP = Tile<BT>::BTP;
   constexpr bool LANEB = Tile<BT>::LANEB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const Geo g = phase_geo(ph);
+  const Geo g = ph.g;
   const int nchunks = (ph.K + KCB - 1) / KCB;
   const int half = ph.K >> 1;
   bool staged = false;
@@ -291,7 +307,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
     if (in) *reinterpret_cast<float4*>(xs + xs_off<BT>(k)) = t;
     __syncthreads();
     staged = true;
-  } else if (ph.pro == PRO_LN && nchunks == 1 && ph.K <= 1024) {
+  } else if (BT > 1 && ph.pro == PRO_LN && nchunks == 1 && ph.K <= 1024) {
     // whole rows fit one pass: warp per sequence, the row stays in registers between the statistics and the staging;
     // two rows in flight per warp
     for (int b0 = warp; b0 < B; b0 += 2 * WPB) {
@@ -438,10 +454,12 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
       for (int kc = 0; kc < nchunks; ++kc) {
         if (nchunks > 1) { __syncthreads(); stage(kc); __syncthreads(); }
         const int k0 = kc * KCB;
+        float red0[MAXSEG], red1[MAXSEG];                 // BT == 1: the units' lane-partial sums, reduced together below
 #pragma unroll
         for (int i = 0; i < MAXSEG; ++i) {
+          red0[i] = 0.f; red1[i] = 0.f;
           const int sw = warp + WPB * i;
-          const int pl = sw / g.KS, ks = sw - pl * g.KS;
+          const int pl = w.pl[i], ks = w.ks[i];
           const int kseg = ks * 256;
           if (pl >= pw || kseg < k0 || kseg >= k0 + KCB) continue;     // warp-uniform
           const int k = kseg + lane * 8;
@@ -465,29 +483,68 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
               }
             }
           }
-          // reduce over lanes: lane b ends with sequence b's sums
-          float* p0 = part + (sw * 2) * BTP;
-          float s0 = 0.f, s1 = 0.f;
+          if constexpr (BT == 1) {
+            red0[i] = acc0[0]; red1[i] = acc1[0];
+          } else {
+            // reduce over lanes: lane b ends with sequence b's sums
+            float* p0 = part + (sw * 2) * BTP;
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < BT; ++j) {
-            const float t0 = warp_sum(acc0[j]), t1 = warp_sum(acc1[j]);
-            if (lane == j) { s0 = t0; s1 = t1; }
+            for (int j = 0; j < BT; ++j) {
+              const float t0 = warp_sum(acc0[j]), t1 = warp_sum(acc1[j]);
+              if (lane == j) { s0 = t0; s1 = t1; }
+            }
+            if (lane < BT) { p0[lane] = s0; p0[BTP + lane] = s1; }
           }
-          if (lane < BT) { p0[lane] = s0; p0[BTP + lane] = s1; }
+        }
+        if constexpr (BT == 1) {
+          // 2 * MAXSEG values per lane -> transposing butterfly: 4 + 2 + 1 exchanges leave value j in the lanes with
+          // (lane & 7) == j summed over their group of 8, two more sum the four groups (9 shuffles instead of 40)
+          static_assert(MAXSEG == 4, "the reduction below is written for 8 values");
+          float v[8] = {red0[0], red1[0], red0[1], red1[1], red0[2], red1[2], red0[3], red1[3]};
+#pragma unroll
+          for (int H = 4; H >= 1; H >>= 1) {
+            const bool up = (lane & H) != 0;
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              const float send = up ? v[j] : v[j + H];
+              const float keep = up ? v[j + H] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+            }
+          }
+          float tot = v[0];
+          tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+          tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+          // lane j < 8 holds value j = unit (j >> 1), row (j & 1) -> part[(warp + WPB * unit) * 2 + row]   (BTP == 1)
+          if (lane < 8) part[(warp + WPB * (lane >> 1)) * 2 + (lane & 1)] = tot;
         }
       }
       __syncthreads();
       prof_mark(pf, 2);
       // finalize this wave's pairs: sum the K segments in order, then the epilogue (threads run over pairs fastest, so
       // the two adjacent output columns of neighbouring pairs coalesce)
-      for (int idx = threadIdx.x; idx < pw * B; idx += TPB) {
-        const int b = idx / pw, pl = idx - b * pw;
-        float s0 = 0.f, s1 = 0.f;
-        for (int ks = 0; ks < g.KS; ++ks) {
-          const float* pp = part + ((pl * g.KS + ks) * 2) * BTP + b;
-          s0 += pp[0]; s1 += pp[BTP];
+      if (BT == 1 && wave == 0) {
+        // this thread's pair, its operands and store addresses were prepared before the barrier (prefetch_phase)
+        const int pl = threadIdx.x;
+        if (pl < pw) {
+          float s0 = pre.b0, s1 = pre.b1;
+          for (int ks = 0; ks < g.KS; ++ks) { s0 += part[(pl * g.KS + ks) * 2]; s1 += part[(pl * g.KS + ks) * 2 + 1]; }
+          if (ph.epi == EP_BIAS) { *pre.d0 = s0; *pre.d1 = s1; }
+          else if (ph.epi == EP_RESIDUAL) { *pre.d0 = pre.o0 + s0; *pre.d1 = pre.o1 + s1; }
+          else if (ph.epi == EP_GELU) { *pre.d0 = gelu_tanh(s0); *pre.d1 = gelu_tanh(s1); }
+          else if (ph.epi == EP_GLU) { *pre.d0 = s0 * gelu_tanh(s1); }
+          else { *pre.d0 = s0 * pre.cs - s1 * pre.sn; *pre.d1 = s1 * pre.cs + s0 * pre.sn; }
         }
-        epilogue(b, g.p_lo + pbase + pl, s0, s1, BT == 1 && wave == 0);
+      } else {
+        for (int idx = threadIdx.x; idx < pw * B; idx += TPB) {
+          const int b = idx / pw, pl = idx - b * pw;
+          float s0 = 0.f, s1 = 0.f;
+          for (int ks = 0; ks < g.KS; ++ks) {
+            const float* pp = part + ((pl * g.KS + ks) * 2) * BTP + b;
+            s0 += pp[0]; s1 += pp[BTP];
+          }
+          epilogue(b, g.p_lo + pbase + pl, s0, s1, false);
+        }
       }
       if (wave + 1 < g.nwaves) __syncthreads();
     } else {
@@ -497,8 +554,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
       __syncthreads();                                       // the previous wave's / phase's readers of wsm are done
 #pragma unroll
       for (int i = 0; i < MAXSEG; ++i) {
-        const int sw = warp + WPB * i;
-        const int pl = sw / g.KS, ks = sw - pl * g.KS;
+        const int pl = w.pl[i], ks = w.ks[i];
         if (pl >= g.PW) continue;
         float a[8], c[8];
         w8_unpack(w.a[i], a);
@@ -872,6 +928,7 @@ __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, b
     ph.wt = L.wqkv_t; ph.bias = nullptr; ph.xin = r.x; ph.ldx = d; ph.out = r.q; ph.ldo = I; ph.N = 3 * I; ph.K = d; ph.epi = EP_ROTARY_CACHE;
     ph.pro = PRO_LN; ph.ln_scale = L.ln1_scale; ph.ln_prev = r.shift_tokens ? L.shift1 : nullptr;
     ph.kcache = L.kcache; ph.vcache = L.vcache; ph.inner = I; ph.dim_head = r.dim_head; ph.n = r.n; ph.rot_sin = r.rot_sin; ph.rot_cos = r.rot_cos;
+    ph.g = make_geo(ph);
     e[0].kind = K_GEMV; e[0].ph = ph; e[0].next = li * 7 + 2;
     ph = Phase{}; ph.kcache = L.kcache; ph.vcache = L.vcache;
     e[1].kind = K_ATT; e[1].ph = ph;
@@ -879,11 +936,13 @@ __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, b
     ph = Phase{};
     ph.wt = L.wo_t; ph.bias = L.bo; ph.xin = r.att; ph.ldx = I; ph.out = r.x; ph.ldo = d; ph.N = d; ph.K = I; ph.epi = EP_RESIDUAL;
     if (att_consumer_merge) { ph.pro = PRO_ATT; ph.aux = r.att_part; ph.window = r.window; ph.dim_head = r.dim_head; }
+    ph.g = make_geo(ph);
     e[2].kind = K_GEMV; e[2].ph = ph; e[2].next = li * 7 + 3;
     // LN + shift + FF-in (+ GLU / GELU)
     ph = Phase{};
     ph.wt = L.win_t; ph.bias = L.bin; ph.xin = r.x; ph.ldx = d; ph.out = r.u; ph.ldo = hid; ph.N = hid; ph.K = d;
     ph.epi = L.kind == 0 ? EP_GLU : EP_GELU; ph.pro = PRO_LN; ph.ln_scale = L.ln2_scale; ph.ln_prev = r.shift_tokens ? L.shift2 : nullptr;
+    ph.g = make_geo(ph);
     e[3].kind = K_GEMV; e[3].ph = ph; e[3].next = li * 7 + (L.kind == 2 ? 5 : 6);
     const float* last = r.u;
     int last_k = hid;
@@ -893,12 +952,14 @@ __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, b
       ph = Phase{};
       ph.wt = L.sgu_proj_t; ph.bias = L.sgu_proj_b; ph.xin = r.u; ph.ldx = hid; ph.out = r.pj; ph.ldo = hid / 2; ph.N = hid / 2; ph.K = hid / 2;
       ph.epi = EP_BIAS; ph.pro = PRO_SGU; ph.aux = r.sg; ph.nsplit = nsplit;
+      ph.g = make_geo(ph);
       e[5].kind = K_GEMV; e[5].ph = ph; e[5].next = li * 7 + 6;
       last = r.pj; last_k = hid / 2;
     }
     // FF-out + residual
     ph = Phase{};
     ph.wt = L.wout_t; ph.bias = L.bout; ph.xin = last; ph.ldx = last_k; ph.out = r.x; ph.ldo = d; ph.N = d; ph.K = last_k; ph.epi = EP_RESIDUAL;
+    ph.g = make_geo(ph);
     e[6].kind = K_GEMV; e[6].ph = ph; e[6].next = li + 1 < r.depth ? (li + 1) * 7 : nph - 2;
   }
   if (threadIdx.x == 0) {
@@ -906,6 +967,7 @@ __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, b
     Phase ph{};
     ph.wt = r.whead_t; ph.bias = r.bhead; ph.xin = r.x; ph.ldx = d; ph.out = r.logits; ph.ldo = r.V; ph.N = r.V; ph.K = d; ph.epi = EP_BIAS;
     ph.pro = PRO_LN; ph.ln_scale = r.lnf_scale; ph.ln_prev = nullptr;
+    ph.g = make_geo(ph);
     tab[nph - 2].kind = K_GEMV; tab[nph - 2].ph = ph; tab[nph - 2].next = 0;
     tab[nph - 1].kind = K_SAMPLE; tab[nph - 1].next = 0; tab[nph - 1].ph = Phase{};
   }
@@ -954,6 +1016,7 @@ __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_
     for (int e = 0; e < nph; ++e) {
       const int kind = tab[e].kind;
       if (kind == K_NONE) continue;
+      bool fetch_next = false;
       if (kind == K_GEMV) {
         Phase ph = tab[e].ph;
         ph.pos = pos;
@@ -961,13 +1024,7 @@ __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_
         prof_mark(pf, 0);
         gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf);
         prof_mark(pf, 3);
-        have = !(e == nph - 2 && step + 1 == r.nsteps);
-        if (have) {
-          Phase nx = tab[tab[e].next].ph;
-          nx.pos = e == nph - 2 ? pos + 1 : pos;               // the head's successor is layer 0 of the next position
-          prefetch_phase<BT, TW>(nx, w, pre);
-        }
-        prof_mark(pf, 4);
+        have = fetch_next = !(e == nph - 2 && step + 1 == r.nsteps);
       } else if (kind == K_ATT) {
         if (MERGE_IN_ATT || !att_consumer) attention_phase<true>(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
         else attention_phase<false>(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
@@ -977,7 +1034,17 @@ __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_
       } else {
         sample_phase(r, pos, xs, red);
       }
-      grid_sync(r.grid_bar, round, pf);
+      // arrive, THEN fetch the next GEMV phase's weights and operands (nothing of it depends on other CTAs' output of
+      // this phase), then wait: the instructions and the loads overlap the barrier's latency
+      long long t0 = 0;
+      grid_arrive(r.grid_bar, round, pf, t0);
+      if (fetch_next) {
+        Phase nx = tab[tab[e].next].ph;
+        nx.pos = e == nph - 2 ? pos + 1 : pos;               // the head's successor is layer 0 of the next position
+        prefetch_phase<BT, TW>(nx, w, pre);
+        prof_mark(pf, 4);
+      }
+      grid_wait(r.grid_bar, round, pf, t0);
     }
   }
 }
