@@ -18,27 +18,53 @@
 // lane keeps 32 activations of its sequence in registers and accumulates its warp's rows, so the FMA pipe, not
 // shared-memory bandwidth, is the bound.  Sequence b samples position p+1 iff p+1 >= start[b] (its prime is kept before).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include "../../include/progen_b200.h"
+#include <type_traits>
 
 namespace {
+
+using namespace tc;
 
 constexpr int TPB = 256, WPB = TPB / 32;
 constexpr int MAXSEG = 4;               // (row pair, 256-column segment) units of weights a warp holds in registers
 constexpr int WSEGS = WPB * MAXSEG;     // segment slots of one CTA per wave
 constexpr int MAXEV = 160;              // profile events per sampled CTA (grid barriers of one step)
 constexpr int MAXSPLIT = 8;             // SGU: most splits of the history range
-template <int BT> struct Tile {         // activation columns staged per pass, by batch tile (shared memory [BT][XP])
-  static constexpr bool LANEB = BT > 8;                       // lane = sequence formulation
-  static constexpr int KCB = BT == 1 ? 8192 : (BT <= 8 ? 2048 : 512);
-  static constexpr int XP = LANEB ? KCB + 4 : KCB;            // row pitch (LANEB: +4 floats -> conflict-free float4 per lane)
+template <int BT, bool TCW = false> struct Tile {   // shared-memory geometry by batch tile; TCW: bf16 weights on the tensor pipe (BT > 8)
+  static constexpr bool LANEB = BT > 8;                       // whole-batch formulations (B > 8)
+  static constexpr bool TC = LANEB && TCW;
+  static constexpr int KCB = BT == 1 ? 8192 : (BT <= 8 ? 2048 : 512);   // activation columns staged per pass
+  // row pitch of the staged activations: +4 floats -> conflict-free float4 per lane (lane = sequence); +8 -> conflict-free
+  // 8-byte A-fragment loads of mma.m16n8k16 (lane = (row, column pair))
+  static constexpr int XP = TC ? KCB + 8 : (LANEB ? KCB + 4 : KCB);
   static constexpr int BTP = BT | 1;                          // odd row pitch of the partial-sum scratch
   static constexpr int STATF = (2 * BT + 2 * WPB + 3) & ~3;   // LN statistics [BT][2] + two block-reduction scratches
-  static constexpr int WSM = LANEB ? WSEGS * 512 : 0;         // LANEB: fp32 copy of one wave's weights [2 * PW rows][256 * KS]
-  static constexpr int PART = LANEB ? 0 : WSEGS * 2 * BTP;    // partial sums of the K segments
-  static constexpr int NBG = LANEB ? BT / 32 : 1;             // LANEB: 32-sequence groups; warp = (group, row split)
+  // one wave's weights: fp32 [2 * PW rows][256 * KS] (lane = sequence), or bf16 [rows][256 * KS + 8] (tensor pipe)
+  static constexpr int WSM = TC ? WSEGS * 256 + 2 * WSEGS * 4 : (LANEB ? WSEGS * 512 : 0);
+  static constexpr int NMT = LANEB ? BT / 16 : 1;             // TC: 16-sequence m-tiles; warp = (m-tile, K split)
+  static constexpr int NKH = LANEB ? WPB / NMT : 1;
+  // partial sums: K segments (B <= 8) | accumulators of the K splits 1.. (tensor pipe) | none (lane = sequence)
+  static constexpr int PART = TC ? (NKH - 1) * NMT * 32 * 32 : (LANEB ? 0 : WSEGS * 2 * BTP);
+  static constexpr int NBG = LANEB ? BT / 32 : 1;             // lane = sequence: 32-sequence groups; warp = (group, row split)
   static constexpr int NRQ = WPB / NBG;
   static constexpr int MAXLP = (WSEGS + NRQ - 1) / NRQ;       // pairs of a wave per row split
 };
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// fp32 pair -> three bf16 pairs whose sum is the fp32 value to 2^-24 (8 + 8 + 8 mantissa bits): with bf16 weights every
+// product is exact in the fp32 accumulator, so the tensor pipe computes the same sums as the fp32 FMA path up to order
+__device__ __forceinline__ void split3_bf16x2(float x0, float x1, uint32_t& h1, uint32_t& h2, uint32_t& h3) {
+  h1 = pack_bf16x2(x0, x1);
+  const float r0 = x0 - __uint_as_float(h1 << 16), r1 = x1 - __uint_as_float(h1 & 0xffff0000u);
+  h2 = pack_bf16x2(r0, r1);
+  const float q0 = r0 - __uint_as_float(h2 << 16), q1 = r1 - __uint_as_float(h2 & 0xffff0000u);
+  h3 = pack_bf16x2(q0, q1);
+}
 
 // ------------------------------------------------------------------------------------------------ grid barrier
 // monotonic counter: every CTA adds 1, then polls until all gridDim.x arrivals of this round are in.  `prof` (optional):
@@ -261,9 +287,11 @@ __device__ __forceinline__ float4 merge_att(const Phase& ph, int k) {
 // One GEMV / skinny-GEMM phase over all B sequences.  BT = compile-time batch tile (B <= BT).  `w`, `pre` hold what
 // prefetch_phase loaded for THIS phase (the caller ran it before the previous grid barrier, or just now).
 template <int BT, typename TW>
-__device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, float* part, float* stat, float* wsm, WRegs<TW>& w, const Pre& pre, const Prof& pf) {
-  constexpr int KCB = Tile<BT>::KCB, XP = Tile<BT>::XP, BTP = Tile<BT>::BTP;
-  constexpr bool LANEB = Tile<BT>::LANEB;
+__device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, float* part, float* stat, float* wsm, WRegs<TW>& w, const Pre& pre, const Prof& pf,
+                                           uint32_t sbar, uint32_t& sparity) {
+  using TL = Tile<BT, sizeof(TW) == 2>;
+  constexpr int KCB = TL::KCB, XP = TL::XP, BTP = TL::BTP;
+  constexpr bool LANEB = TL::LANEB, TC = TL::TC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Geo g = ph.g;
   const int nchunks = (ph.K + KCB - 1) / KCB;
@@ -309,54 +337,64 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
     staged = true;
   } else if (BT > 1 && ph.pro == PRO_LN && nchunks == 1 && ph.K <= 1024) {
     // whole rows fit one pass: warp per sequence, the row stays in registers between the statistics and the staging;
-    // two rows in flight per warp
-    for (int b0 = warp; b0 < B; b0 += 2 * WPB) {
-      float4 v[2][8];
+    // RF rows (NJ float4 per lane each) in flight per warp
+    auto ln_rows = [&](auto rf_c, auto nj_c) {
+      constexpr int RF = decltype(rf_c)::value, NJ = decltype(nj_c)::value;
+      for (int b0 = warp; b0 < B; b0 += RF * WPB) {
+        float4 v[RF][NJ], pvv[RF][NJ / 2];                  // the rows and their token-shift state (first half of the columns)
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int b = b0 + rr * WPB;
+        for (int rr = 0; rr < RF; ++rr) {
+          const int b = b0 + rr * WPB;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = j * 128 + lane * 4;
-          v[rr][j] = (b < B && k < ph.K) ? __ldcg(reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
+          for (int j = 0; j < NJ; ++j) {
+            const int k = j * 128 + lane * 4;
+            v[rr][j] = (b < B && k < ph.K) ? __ldcg(reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int b = b0 + rr * WPB;
-        if (b >= B) continue;
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += (v[rr][j].x + v[rr][j].y) + (v[rr][j].z + v[rr][j].w);
-        const float mean = warp_sum(s) / ph.K;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j * 128 + lane * 4 < ph.K) {
-            const float a0 = v[rr][j].x - mean, a1 = v[rr][j].y - mean, a2 = v[rr][j].z - mean, a3 = v[rr][j].w - mean;
-            q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          for (int j = 0; j < NJ / 2; ++j) {
+            const int k = j * 128 + lane * 4;
+            pvv[rr][j] = (ph.ln_prev && b < B && k < half)
+                             ? __ldcg(reinterpret_cast<const float4*>(ph.ln_prev + (long long)b * ph.K + (ph.pos & 1) * half + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        const float rstd = rsqrtf(warp_sum(q) / ph.K + 1e-5f);
-        float* st = ph.ln_prev ? ph.ln_prev + (long long)b * ph.K : nullptr;       // [2][K/2]
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = j * 128 + lane * 4;
-          if (k < ph.K) {
-            const float4 sc = *reinterpret_cast<const float4*>(ph.ln_scale + k);
-            float4 t;
-            t.x = (v[rr][j].x - mean) * rstd * sc.x; t.y = (v[rr][j].y - mean) * rstd * sc.y;
-            t.z = (v[rr][j].z - mean) * rstd * sc.z; t.w = (v[rr][j].w - mean) * rstd * sc.w;
-            if (st && k < half) {
-              const float4 pv = __ldcg(reinterpret_cast<const float4*>(st + (ph.pos & 1) * half + k));
-              if (blockIdx.x == 0) *reinterpret_cast<float4*>(st + ((ph.pos + 1) & 1) * half + k) = t;
-              t = pv;
+        for (int rr = 0; rr < RF; ++rr) {
+          const int b = b0 + rr * WPB;
+          if (b >= B) continue;
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) s += (v[rr][j].x + v[rr][j].y) + (v[rr][j].z + v[rr][j].w);
+          const float mean = warp_sum(s) / ph.K;
+          float q = 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            if (j * 128 + lane * 4 < ph.K) {
+              const float a0 = v[rr][j].x - mean, a1 = v[rr][j].y - mean, a2 = v[rr][j].z - mean, a3 = v[rr][j].w - mean;
+              q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
             }
-            *reinterpret_cast<float4*>(xs + b * XP + xs_off<BT>(k)) = t;
+          }
+          const float rstd = rsqrtf(warp_sum(q) / ph.K + 1e-5f);
+          float* st = ph.ln_prev ? ph.ln_prev + (long long)b * ph.K : nullptr;       // [2][K/2]
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int k = j * 128 + lane * 4;
+            if (k < ph.K) {
+              const float4 sc = *reinterpret_cast<const float4*>(ph.ln_scale + k);
+              float4 t;
+              t.x = (v[rr][j].x - mean) * rstd * sc.x; t.y = (v[rr][j].y - mean) * rstd * sc.y;
+              t.z = (v[rr][j].z - mean) * rstd * sc.z; t.w = (v[rr][j].w - mean) * rstd * sc.w;
+              if (st && k < half) {                         // k < half  =>  j < NJ / 2 (half = K / 2 <= NJ * 64)
+                if (blockIdx.x == 0) *reinterpret_cast<float4*>(st + ((ph.pos + 1) & 1) * half + k) = t;
+                t = pvv[rr][j < NJ / 2 ? j : 0];
+              }
+              *reinterpret_cast<float4*>(xs + b * XP + xs_off<BT>(k)) = t;
+            }
           }
         }
       }
-    }
+    };
+    if (ph.K <= 512) ln_rows(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
+    else ln_rows(std::integral_constant<int, 2>{}, std::integral_constant<int, 8>{});
     __syncthreads();
     staged = true;
   } else if (ph.pro == PRO_LN) {
@@ -378,22 +416,21 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
     }
     __syncthreads();
   }
-  // stage x[:, k0 .. k0+kn) (with the prologue) into shared memory; four independent loads in flight per thread
-  auto stage = [&](int kc) {
+  // stage x[:, k0 .. k0+kn) (with the prologue) into shared memory; U independent loads in flight per thread
+  constexpr int U = LANEB ? 16 : 4;
+  auto stage_regs = [&](int kc) {
     const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
     const int nvec = B * (kn >> 2);
-    for (int base = 0; base < nvec; base += 4 * TPB) {
-      float4 t[4];
+    for (int base = 0; base < nvec; base += U * TPB) {
+      float4 t[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * TPB + threadIdx.x;
-        if (idx < nvec) {
-          const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
-          t[u] = __ldcg(reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k0 + k));
-        }
+      for (int u = 0; u < U; ++u) {
+        const int idx = min(base + u * TPB + (int)threadIdx.x, nvec - 1);       // clamped: the load is unconditional
+        const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
+        t[u] = __ldcg(reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k0 + k));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int idx = base + u * TPB + threadIdx.x;
         if (idx >= nvec) continue;
         const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
@@ -409,16 +446,56 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
             if (blockIdx.x == 0) *reinterpret_cast<float4*>(st + ((ph.pos + 1) & 1) * half + k0 + k) = v;
             v = pv;
           }
-        } else if (ph.pro == PRO_SGU) {
-          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int s = 0; s < ph.nsplit; ++s) {
-            const float4 q = __ldcg(reinterpret_cast<const float4*>(ph.aux + ((long long)s * B + b) * ph.K + k0 + k));
-            gsum.x += q.x; gsum.y += q.y; gsum.z += q.z; gsum.w += q.w;
-          }
-          v.x *= gsum.x; v.y *= gsum.y; v.z *= gsum.z; v.w *= gsum.w;
         }
         *reinterpret_cast<float4*>(xs + b * XP + xs_off<BT>(k)) = v;
       }
+    }
+  };
+  // PRO_SGU: x = xs * (sum of the partial gates); the activations and split 0's gate are loaded together
+  auto stage_sgu = [&](int kc) {
+    constexpr int U2 = LANEB ? 8 : 4;
+    const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
+    const int nvec = B * (kn >> 2);
+    for (int base = 0; base < nvec; base += U2 * TPB) {
+      float4 t[U2], gq[U2];
+#pragma unroll
+      for (int u = 0; u < U2; ++u) {
+        const int idx = min(base + u * TPB + (int)threadIdx.x, nvec - 1);
+        const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
+        t[u] = __ldcg(reinterpret_cast<const float4*>(ph.xin + (long long)b * ph.ldx + k0 + k));
+        gq[u] = __ldcg(reinterpret_cast<const float4*>(ph.aux + (long long)b * ph.K + k0 + k));
+      }
+#pragma unroll
+      for (int u = 0; u < U2; ++u) {
+        const int idx = base + u * TPB + threadIdx.x;
+        if (idx >= nvec) continue;
+        const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
+        float4 gsum = gq[u];
+        for (int sp = 1; sp < ph.nsplit; ++sp) {
+          const float4 q = __ldcg(reinterpret_cast<const float4*>(ph.aux + ((long long)sp * B + b) * ph.K + k0 + k));
+          gsum.x += q.x; gsum.y += q.y; gsum.z += q.z; gsum.w += q.w;
+        }
+        *reinterpret_cast<float4*>(xs + b * XP + xs_off<BT>(k)) = make_float4(t[u].x * gsum.x, t[u].y * gsum.y, t[u].z * gsum.z, t[u].w * gsum.w);
+      }
+    }
+  };
+  // B > 8, no prologue: one bulk copy (L2 -> shared memory, no registers, no L1) per sequence row
+  auto stage = [&](int kc) {
+    if (LANEB && ph.pro == PRO_NONE) {
+      const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
+      fence_proxy_async();                                  // earlier generic accesses to xs are ordered before the async writes
+      __syncthreads();
+      if (threadIdx.x == 0) mbar_expect_tx(sbar, (uint32_t)(B * kn * 4));
+      if (threadIdx.x < B) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(xs + threadIdx.x * XP)), "l"(ph.xin + (long long)threadIdx.x * ph.ldx + k0), "r"((uint32_t)(kn * 4)), "r"(sbar) : "memory");
+      }
+      mbar_wait(sbar, sparity);
+      sparity ^= 1u;
+    } else if (ph.pro == PRO_SGU) {
+      stage_sgu(kc);
+    } else {
+      stage_regs(kc);
     }
   };
   // bias + activation / residual / rotary + cache for the two rows of `pair` of sequence b
@@ -548,8 +625,135 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
       }
       if (wave + 1 < g.nwaves) __syncthreads();
     } else {
+      if constexpr (TC) {
+        // ---- tensor pipe (bf16 weights).  (1) this wave's weights -> shared memory as they are: bf16 [row = 2*pl + which][WK + 8]
+        constexpr int NMT = TL::NMT, NKH = TL::NKH, NTMAX = 2 * WSEGS / 8;
+        const int WK = g.KS * 256, WKP = WK + 8;               // +8 bf16: the 8 rows of a B fragment land in distinct banks
+        __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(wsm);
+        __syncthreads();                                       // the previous wave's / phase's readers of wsm are done
+#pragma unroll
+        for (int i = 0; i < MAXSEG; ++i) {
+          const int pl = w.pl[i], ks = w.ks[i];
+          if (pl >= g.PW) continue;
+          __nv_bfloat16* d0 = wb + (2 * pl) * WKP + ks * 256 + lane * 8;
+          *reinterpret_cast<uint4*>(d0) = w.a[i].q[0];
+          *reinterpret_cast<uint4*>(d0 + WKP) = w.c[i].q[0];
+        }
+        // (2) warp = (m-tile of 16 sequences, K split): C[16 x 8 per n-tile] += A[16 x 16](x, three bf16 terms) B[16 x 8](weights)
+        const int mt = warp % NMT, kh = warp / NMT;
+        const int NT = (2 * pw + 7) >> 3;                      // n-tiles of 8 weight rows
+        const int gr = lane >> 2, gc = (lane & 3) * 2;
+        float acc[NTMAX][4];
+#pragma unroll
+        for (int nt = 0; nt < NTMAX; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+        for (int kc = 0; kc < nchunks; ++kc) {
+          __syncthreads();                                     // wsm written (kc == 0) / the previous chunk's xs readers done
+          if (kc == 0) prof_mark(pf, 5);
+          if (nchunks > 1) { stage(kc); __syncthreads(); }
+          const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
+          const float* xa = xs + (mt * 16 + gr) * XP + gc;
+#pragma unroll 2
+          for (int kb = kh * 16; kb < kn; kb += NKH * 16) {
+            uint32_t a1[4], a2[4], a3[4];
+            {
+              const float2 v0 = *reinterpret_cast<const float2*>(xa + kb);
+              const float2 v1 = *reinterpret_cast<const float2*>(xa + 8 * XP + kb);
+              const float2 v2 = *reinterpret_cast<const float2*>(xa + kb + 8);
+              const float2 v3 = *reinterpret_cast<const float2*>(xa + 8 * XP + kb + 8);
+              split3_bf16x2(v0.x, v0.y, a1[0], a2[0], a3[0]);
+              split3_bf16x2(v1.x, v1.y, a1[1], a2[1], a3[1]);
+              split3_bf16x2(v2.x, v2.y, a1[2], a2[2], a3[2]);
+              split3_bf16x2(v3.x, v3.y, a1[3], a2[3], a3[3]);
+            }
+            const __nv_bfloat16* wk = wb + gr * WKP + k0 + kb + gc;
+            uint32_t fb0[NTMAX], fb1[NTMAX];
+#pragma unroll
+            for (int nt = 0; nt < NTMAX; ++nt) {
+              const int nn = nt < NT ? nt : 0;                 // (clamped: unconditional loads)
+              fb0[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP);
+              fb1[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP + 8);
+            }
+            // term-major, smallest terms first: consecutive MMAs hit different accumulators
+#pragma unroll
+            for (int nt = 0; nt < NTMAX; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a3, fb0[nt], fb1[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NTMAX; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a2, fb0[nt], fb1[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NTMAX; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a1, fb0[nt], fb1[nt]);
+          }
+        }
+        prof_mark(pf, 6);
+        // (3) K splits 1.. -> shared memory, split 0 adds them in order, then the epilogue from its registers:
+        // lane holds (sequence gr | gr + 8 of the m-tile) x (weight rows 8 nt + gc, + 1 = the two rows of pair 4 nt + gc / 2)
+        if (kh > 0) {
+#pragma unroll
+          for (int nt = 0; nt < NTMAX; ++nt)
+            if (nt < NT) *reinterpret_cast<float4*>(part + ((kh - 1) * NMT + mt) * 1024 + nt * 128 + lane * 4) =
+                make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
+        }
+        __syncthreads();
+        prof_mark(pf, 2);
+        if (kh == 0) {
+          // every operand of the epilogue first (bias, old residual values, rotary entries: independent loads), then the math
+          const int b0 = mt * 16 + gr;
+          float bia[NTMAX][2], old[NTMAX][4], rot[NTMAX][2];
+#pragma unroll
+          for (int nt = 0; nt < NTMAX; ++nt) {
+            const int pl = nt * 4 + (lane & 3);
+            const bool v = nt < NT && pl < pw;
+            const int pair = g.p_lo + pbase + (v ? pl : 0);
+            const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+            bia[nt][0] = ph.bias ? ph.bias[r0] : 0.f;
+            bia[nt][1] = ph.bias ? ph.bias[r1] : 0.f;
+            old[nt][0] = old[nt][1] = old[nt][2] = old[nt][3] = 0.f;
+            if (ph.epi == EP_RESIDUAL) {
+              const float* o0 = ph.out + (long long)(b0 < B ? b0 : 0) * ph.ldo;
+              const float* o1 = ph.out + (long long)(b0 + 8 < B ? b0 + 8 : 0) * ph.ldo;
+              old[nt][0] = __ldcg(o0 + r0); old[nt][1] = __ldcg(o0 + r1);
+              old[nt][2] = __ldcg(o1 + r0); old[nt][3] = __ldcg(o1 + r1);
+            }
+            rot[nt][0] = rot[nt][1] = 0.f;
+            if (ph.epi == EP_ROTARY_CACHE) {
+              const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
+              rot[nt][0] = ph.rot_sin[ph.pos * hd + j]; rot[nt][1] = ph.rot_cos[ph.pos * hd + j];
+            }
+          }
+#pragma unroll
+          for (int nt = 0; nt < NTMAX; ++nt) {
+            if (nt < NT) {
+#pragma unroll
+              for (int q = 1; q < NKH; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(part + ((q - 1) * NMT + mt) * 1024 + nt * 128 + lane * 4);
+                acc[nt][0] += v.x; acc[nt][1] += v.y; acc[nt][2] += v.z; acc[nt][3] += v.w;
+              }
+              const int pl = nt * 4 + (lane & 3);
+              if (pl < pw) {
+                const int pair = g.p_lo + pbase + pl;
+                const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                  const int b = b0 + 8 * hb;
+                  if (b >= B) continue;
+                  const float s0 = acc[nt][2 * hb] + bia[nt][0], s1 = acc[nt][2 * hb + 1] + bia[nt][1];
+                  float* o = ph.out + (long long)b * ph.ldo;
+                  if (ph.epi == EP_BIAS) { o[r0] = s0; o[r1] = s1; }
+                  else if (ph.epi == EP_RESIDUAL) { o[r0] = old[nt][2 * hb] + s0; o[r1] = old[nt][2 * hb + 1] + s1; }
+                  else if (ph.epi == EP_GELU) { o[r0] = gelu_tanh(s0); o[r1] = gelu_tanh(s1); }
+                  else if (ph.epi == EP_GLU) { o[r0] = s0 * gelu_tanh(s1); }
+                  else {
+                    const float sn = rot[nt][0], cs = rot[nt][1];
+                    const int sec = r0 / ph.inner, c = r0 % ph.inner;
+                    float* dst = sec == 0 ? o + c : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)b * ph.n + ph.pos) * ph.inner + c;
+                    dst[0] = s0 * cs - s1 * sn; dst[1] = s1 * cs + s0 * sn;
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else {
       // ---- lane = sequence.  (1) this wave's weights -> shared memory as fp32 [row = 2*pl + which][256*KS columns]
-      constexpr int NBG = Tile<BT>::NBG, NRQ = Tile<BT>::NRQ, MAXLP = Tile<BT>::MAXLP;
+      constexpr int NBG = TL::NBG, NRQ = TL::NRQ, MAXLP = TL::MAXLP;
       const int WK = g.KS * 256;                             // columns per staged row (tail zero-filled by load_wave)
       __syncthreads();                                       // the previous wave's / phase's readers of wsm are done
 #pragma unroll
@@ -613,6 +817,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
           const int pl = q + NRQ * lp;
           if (pl < pw) epilogue(b, g.p_lo + pbase + pl, acc[lp][0][0] + acc[lp][0][1], acc[lp][1][0] + acc[lp][1][1], false);
         }
+      }
       }
     }
   }
@@ -730,6 +935,117 @@ __device__ void attention_phase_t(const progen_decode_run_t& r, const float* kca
         if (lane == 0) r.att_count[bh] = 0;
       }
     }
+  }
+}
+
+// B > 1: WP warps (1, 2, 4 or 8, all of one CTA) own one (sequence, head): each walks its share of the 32-key slices with a
+// running (max, sum, out) and the WP partials are merged through shared memory — no global partials, no atomics, no fences.
+template <int NL>
+__device__ void attention_batch_t(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq /* smem >= WPB * (dh + 4) + WPB * dh */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int dh = NL * 4, KG = 32 / NL, NH = NL >= 2 ? NL / 2 : 1;
+  const int w = r.window, I = r.inner;
+  const int win = pos / w, i = pos % w;
+  const int key0 = win > 0 ? (win - 1) * w : 0;
+  const int nreal = (win > 0 ? w : 0) + i + 1;
+  const int nsl = (nreal + 31) / 32;
+  const int npairs = r.B * r.heads;
+  int WP = 8;
+  while (WP > 1 && (long long)npairs * WP > (long long)gridDim.x * WPB) WP >>= 1;
+  const int slots = WPB / WP, slot = warp / WP, sub = warp % WP;
+  const int rounds = (npairs + gridDim.x * slots - 1) / (gridDim.x * slots);
+  const float scale = rsqrtf((float)dh);
+  const int kg = lane / NL, c4 = (lane % NL) * 4;
+  float* q_s = sq + warp * dh;                                // this warp's copy of q
+  float* mrg = sq + WPB * dh;                                 // [WPB][dh + 4] partials
+  for (int rnd = 0; rnd < rounds; ++rnd) {
+    const int pr = (rnd * slots + slot) * gridDim.x + blockIdx.x;
+    const bool on = pr < npairs;
+    const int hh = on ? pr % r.heads : 0, b = on ? pr / r.heads : 0;
+    float m = -INFINITY, lsum = 0.f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      const float* qv = r.q + (long long)b * I + hh * dh;
+      if (lane < NL) *reinterpret_cast<float4*>(q_s + lane * 4) = __ldcg(reinterpret_cast<const float4*>(qv + lane * 4));
+      __syncwarp();
+      for (int sl = sub; sl < nsl; sl += WP) {
+        const int j = sl * 32 + lane;
+        const bool valid = j < nreal;
+        const int nk = min(32, nreal - sl * 32);
+        const float* kr = kcache + ((long long)b * r.n + key0 + (valid ? j : 0)) * I + hh * dh;
+        const float* vb = vcache + ((long long)b * r.n + key0 + sl * 32) * I + hh * dh + c4;
+        float4 kreg[NL], vreg[NH];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) kreg[c] = __ldcg(reinterpret_cast<const float4*>(kr + c * 4));
+#pragma unroll
+        for (int jj = 0; jj < NH; ++jj) {
+          const int key = kg + jj * KG;
+          vreg[jj] = key < nk ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+          const float4 qq = *reinterpret_cast<const float4*>(q_s + c * 4);
+          s = fmaf(kreg[c].x, qq.x, s); s = fmaf(kreg[c].y, qq.y, s); s = fmaf(kreg[c].z, qq.z, s); s = fmaf(kreg[c].w, qq.w, s);
+        }
+        float4 vreg2[NH];
+#pragma unroll
+        for (int jj = 0; jj < NH; ++jj) {
+          const int key = kg + (jj + NH) * KG;
+          vreg2[jj] = (NH + jj < NL && key < nk) ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        s = valid ? s * scale : -INFINITY;
+        const float mn = fmaxf(m, warp_max(s));               // finite: every slice has at least one real key
+        const float f = expf(m - mn);                          // 0 for the first slice (m = -inf)
+        const float pv = valid ? expf(s - mn) : 0.f;
+        lsum = lsum * f + pv;
+        o.x *= f; o.y *= f; o.z *= f; o.w *= f;
+        m = mn;
+#pragma unroll
+        for (int jj = 0; jj < NL; ++jj) {
+          const int key = kg + jj * KG;
+          const float pj = __shfl_sync(0xffffffffu, pv, key & 31);
+          const float4 vv = jj < NH ? vreg[jj % NH] : vreg2[jj % NH];
+          o.x = fmaf(pj, vv.x, o.x); o.y = fmaf(pj, vv.y, o.y); o.z = fmaf(pj, vv.z, o.z); o.w = fmaf(pj, vv.w, o.w);
+        }
+      }
+      for (int off = NL; off < 32; off <<= 1) {
+        o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
+        o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
+      }
+      lsum = warp_sum(lsum);
+      float* pt = mrg + warp * (dh + 4);
+      if (lane < NL) *reinterpret_cast<float4*>(pt + 4 + lane * 4) = o;
+      if (lane == 0) { pt[0] = m; pt[1] = lsum; }
+    }
+    __syncthreads();
+    if (on && sub == 0 && lane < NL) {
+      // merge the WP partials (a warp with no slice left m = -inf, l = 0) plus window 0's w zero keys with logit 0 (quirk Q1)
+      const float* pb = mrg + (slot * WP) * (dh + 4);
+      float M = win == 0 ? 0.f : -INFINITY;
+      for (int k = 0; k < WP; ++k) M = fmaxf(M, pb[k * (dh + 4)]);
+      float Lt = win == 0 ? (float)w * expf(-M) : 0.f;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < WP; ++k) {
+        const float* pk = pb + k * (dh + 4);
+        const float f = expf(pk[0] - M);
+        Lt = fmaf(pk[1], f, Lt);
+        const float4 ov = *reinterpret_cast<const float4*>(pk + 4 + lane * 4);
+        a.x = fmaf(f, ov.x, a.x); a.y = fmaf(f, ov.y, a.y); a.z = fmaf(f, ov.z, a.z); a.w = fmaf(f, ov.w, a.w);
+      }
+      const float inv = 1.f / Lt;
+      *reinterpret_cast<float4*>(r.att + (long long)b * I + hh * dh + lane * 4) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+    }
+    __syncthreads();
+  }
+}
+__device__ void attention_batch(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq) {
+  switch (r.dim_head) {
+    case 64: attention_batch_t<16>(r, kcache, vcache, pos, sq); break;
+    case 32: attention_batch_t<8>(r, kcache, vcache, pos, sq); break;
+    case 16: attention_batch_t<4>(r, kcache, vcache, pos, sq); break;
+    case 8: attention_batch_t<2>(r, kcache, vcache, pos, sq); break;
+    default: attention_batch_t<1>(r, kcache, vcache, pos, sq); break;
   }
 }
 
@@ -974,24 +1290,30 @@ __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, b
   __syncthreads();
 }
 
-template <int BT> constexpr size_t decode_smem_floats() {
-  return (size_t)BT * Tile<BT>::XP + Tile<BT>::PART + Tile<BT>::STATF + Tile<BT>::WSM + WPB * 128 + 64;
+template <int BT, bool TCW> constexpr size_t decode_smem_floats() {
+  using TL = Tile<BT, TCW>;
+  return (size_t)BT * TL::XP + TL::PART + TL::STATF + TL::WSM + WPB * 128 + 64;
 }
 
 template <int BT, typename TW>
 __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_decode_run_t r) {
   extern __shared__ __align__(16) float smem[];
+  using TL = Tile<BT, sizeof(TW) == 2>;
   float* xs = smem;                                    // [BT][XP]
-  float* part = xs + BT * Tile<BT>::XP;                // partial sums
-  float* stat = part + Tile<BT>::PART;                 // [STATF]
-  float* wsm = stat + Tile<BT>::STATF;                 // lane = sequence: fp32 weights of one wave
-  float* red = wsm + Tile<BT>::WSM;                    // scratch of the other phases: WPB * 128 + 64
+  float* part = xs + BT * TL::XP;                      // partial sums
+  float* stat = part + TL::PART;                       // [STATF]
+  float* wsm = stat + TL::STATF;                       // B > 8: one wave's weights
+  float* red = wsm + TL::WSM;                          // scratch of the other phases: WPB * 128 + 64
   PhaseEnt* tab = reinterpret_cast<PhaseEnt*>(red + WPB * 128 + 64);
+  __shared__ __align__(8) uint64_t stage_bar;
+  const uint32_t sbar = smem_u32(&stage_bar);
+  uint32_t sparity = 0;
+  if (threadIdx.x == 0) { mbar_init(sbar, 1); fence_barrier_init(); }
   const int nph = num_phases(r.depth);
   constexpr bool MERGE_IN_ATT = BT > 1;
   const bool att_consumer = !MERGE_IN_ATT && r.inner <= 4 * TPB;
   build_phase_table(r, tab, att_consumer, sgu_splits(r));
-  for (int i = threadIdx.x; i < BT * Tile<BT>::XP; i += TPB) xs[i] = 0.f;     // tails beyond K are multiplied by zero weights: keep them finite
+  for (int i = threadIdx.x; i < BT * TL::XP; i += TPB) xs[i] = 0.f;     // tails beyond K are multiplied by zero weights: keep them finite
   __syncthreads();
   unsigned int round = 0;
   const int d = r.d, B = r.B;
@@ -1022,11 +1344,11 @@ __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_
         ph.pos = pos;
         if (!have) prefetch_phase<BT, TW>(ph, w, pre);
         prof_mark(pf, 0);
-        gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf);
+        gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf, sbar, sparity);
         prof_mark(pf, 3);
         have = fetch_next = !(e == nph - 2 && step + 1 == r.nsteps);
       } else if (kind == K_ATT) {
-        if (MERGE_IN_ATT || !att_consumer) attention_phase<true>(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
+        if (MERGE_IN_ATT || !att_consumer) attention_batch(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
         else attention_phase<false>(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
       } else if (kind == K_SGU) {
         const SguArgs sa{tab[e].ph.ln_scale, reinterpret_cast<const float*>(tab[e].ph.wt), tab[e].ph.bias, tab[e].ph.kcache};
@@ -1051,8 +1373,9 @@ __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_
 
 template <int BT, typename TW>
 int launch_run(const progen_decode_run_t& r, cudaStream_t s) {
-  static_assert((BT * Tile<BT>::XP) % 4 == 0 && Tile<BT>::PART % 4 == 0 && Tile<BT>::WSM % 4 == 0, "the scratch regions must stay 16-byte aligned");
-  const size_t smem = decode_smem_floats<BT>() * sizeof(float) + (size_t)num_phases(r.depth) * sizeof(PhaseEnt);
+  using TL = Tile<BT, sizeof(TW) == 2>;
+  static_assert((BT * TL::XP) % 4 == 0 && TL::PART % 4 == 0 && TL::WSM % 4 == 0, "the scratch regions must stay 16-byte aligned");
+  const size_t smem = decode_smem_floats<BT, sizeof(TW) == 2>() * sizeof(float) + (size_t)num_phases(r.depth) * sizeof(PhaseEnt);
   PG_CHECK_ARG(smem <= 227 * 1024);
   auto kern = decode_persistent_kernel<BT, TW>;
   static size_t set_for = 0;

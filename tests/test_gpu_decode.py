@@ -99,6 +99,32 @@ def test_persistent_logits_match_oracle_forward():
     assert np.abs(got[:n - 1] - ref[:n - 1]).max() < 2e-5 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize('B,wdt', [(33, 'bf16'), (20, 'bf16'), (40, 'f32')])
+def test_batched_logits_match_oracle_forward(B, wdt):
+    """B > 8 paths (bf16 weights: mma.sync with the activations split into three bf16 terms; fp32 weights: lane = sequence
+    FMAs): every sequence's logits against the oracle's full forward of the sequence it ended with.  With bf16 weights the
+    oracle runs on the bf16-rounded weights, so the bound stays at fp32 round-off."""
+    import torch
+    from progen_b200.decode import BatchDecoder
+    from oracle import progen_ref as O
+    cfg, params, data, g = load_case('tiny_glu_sgu')
+    rng = np.random.default_rng(100 + B)
+    primes = [rng.integers(1, 256, int(rng.integers(1, 9))).astype(np.int64) for _ in range(B)]
+    dt = torch.bfloat16 if wdt == 'bf16' else torch.float32
+    dec = BatchDecoder(cfg, params, batch=B, weights_dtype=dt, keep_logits=True)
+    dec.sample(primes, top_k=25, add_bos=True, greedy=True)
+    seqs = dec.seq.cpu().numpy().astype(np.int64)
+    got = dec.logits_all.cpu().numpy()
+    ref_params = params
+    if wdt == 'bf16':
+        rnd = lambda a: torch.tensor(np.asarray(a, np.float32)).bfloat16().float().numpy()
+        ref_params = {k: {kk: (rnd(vv) if kk == 'w' else vv) for kk, vv in v.items()} for k, v in params.items()}
+    n = cfg['seq_len']
+    for b in (0, B // 2, B - 1):
+        ref = O.forward(ref_params, np.clip(seqs[b], 0, 255), cfg)
+        assert np.abs(got[b, :n - 1] - ref[:n - 1]).max() < 3e-5 * max(1.0, np.abs(ref).max()), b
+
+
 @pytest.mark.parametrize('B', [3, 8, 33])
 def test_batched_decode_equals_single_stream(B):
     """B primes of different lengths decoded in lock step == each prime decoded alone (greedy, bit-equal ids)"""
