@@ -26,11 +26,21 @@ namespace {
 
 using namespace tc;
 
-constexpr int TPB = 256, WPB = TPB / 32;
-constexpr int MAXSEG = 4;               // (row pair, 256-column segment) units of weights a warp holds in registers
-constexpr int WSEGS = WPB * MAXSEG;     // segment slots of one CTA per wave
+constexpr int WSEGS = 32;               // (row pair, 256-column segment) weight units of one CTA per wave
 constexpr int MAXEV = 160;              // profile events per sampled CTA (grid barriers of one step)
 constexpr int MAXSPLIT = 8;             // SGU: most splits of the history range
+// threads per CTA by batch tile.  A single sequence is a latency chain: 8 warps are enough.  For B > 8 both 256 threads (255
+// registers) and 512 (128 registers, some spills) were measured: 31.6 k tokens/s at B = 64 either way — the phases are bound by
+// L2 traffic of the activation staging and by memory latency, not by issue slots — so the default is the spill-free one.
+#ifndef PROGEN_DECODE_BATCH_THREADS
+#define PROGEN_DECODE_BATCH_THREADS 256
+#endif
+constexpr int threads_for(int BT) { return BT > 8 ? PROGEN_DECODE_BATCH_THREADS : 256; }
+
+template <int TPB> struct Impl {
+static constexpr int WPB = TPB / 32;
+static constexpr int MAXSEG = WSEGS / WPB;   // units a warp holds in registers
+
 template <int BT, bool TCW = false> struct Tile {   // shared-memory geometry by batch tile; TCW: bf16 weights on the tensor pipe (BT > 8)
   static constexpr bool LANEB = BT > 8;                       // whole-batch formulations (B > 8)
   static constexpr bool TC = LANEB && TCW;
@@ -44,21 +54,22 @@ template <int BT, bool TCW = false> struct Tile {   // shared-memory geometry by
   static constexpr int WSM = TC ? WSEGS * 256 + 2 * WSEGS * 4 : (LANEB ? WSEGS * 512 : 0);
   static constexpr int NMT = LANEB ? BT / 16 : 1;             // TC: 16-sequence m-tiles; warp = (m-tile, K split)
   static constexpr int NKH = LANEB ? WPB / NMT : 1;
-  // partial sums: K segments (B <= 8) | accumulators of the K splits 1.. (tensor pipe) | none (lane = sequence)
-  static constexpr int PART = TC ? (NKH - 1) * NMT * 32 * 32 : (LANEB ? 0 : WSEGS * 2 * BTP);
+  // partial sums: K segments (B <= 8) | accumulators of the upper half of the K splits, halved round by round (tensor pipe) |
+  // none (lane = sequence)
+  static constexpr int PART = TC ? (NKH / 2) * NMT * 32 * 32 : (LANEB ? 0 : WSEGS * 2 * BTP);
   static constexpr int NBG = LANEB ? BT / 32 : 1;             // lane = sequence: 32-sequence groups; warp = (group, row split)
   static constexpr int NRQ = WPB / NBG;
   static constexpr int MAXLP = (WSEGS + NRQ - 1) / NRQ;       // pairs of a wave per row split
 };
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+static __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // fp32 pair -> three bf16 pairs whose sum is the fp32 value to 2^-24 (8 + 8 + 8 mantissa bits): with bf16 weights every
 // product is exact in the fp32 accumulator, so the tensor pipe computes the same sums as the fp32 FMA path up to order
-__device__ __forceinline__ void split3_bf16x2(float x0, float x1, uint32_t& h1, uint32_t& h2, uint32_t& h3) {
+static __device__ __forceinline__ void split3_bf16x2(float x0, float x1, uint32_t& h1, uint32_t& h2, uint32_t& h3) {
   h1 = pack_bf16x2(x0, x1);
   const float r0 = x0 - __uint_as_float(h1 << 16), r1 = x1 - __uint_as_float(h1 & 0xffff0000u);
   h2 = pack_bf16x2(r0, r1);
@@ -71,10 +82,10 @@ __device__ __forceinline__ void split3_bf16x2(float x0, float x1, uint32_t& h1, 
 // CTA 0 and the last CTA record clock64 at entry and exit of every barrier of the launch's LAST step.
 struct Prof { long long* buf; int ev; bool on; };
 // CTA 0, thread 0: clock64 at point k (< 8) inside the phase that ends with barrier number pf.ev  (buf + 4 * MAXEV: [MAXEV][8])
-__device__ __forceinline__ void prof_mark(const Prof& pf, int k) {
+static __device__ __forceinline__ void prof_mark(const Prof& pf, int k) {
   if (pf.on && blockIdx.x == 0 && threadIdx.x == 0 && pf.ev < MAXEV) pf.buf[4 * MAXEV + pf.ev * 8 + k] = clock64();
 }
-__device__ __forceinline__ void grid_arrive(unsigned int* bar, unsigned int& round, Prof& pf, long long& t0) {
+static __device__ __forceinline__ void grid_arrive(unsigned int* bar, unsigned int& round, Prof& pf, long long& t0) {
   __syncthreads();
   if (threadIdx.x == 0) {
     if (pf.on) t0 = clock64();
@@ -83,7 +94,7 @@ __device__ __forceinline__ void grid_arrive(unsigned int* bar, unsigned int& rou
     atomicAdd(bar, 1u);
   }
 }
-__device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int round, Prof& pf, long long t0) {
+static __device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int round, Prof& pf, long long t0) {
   if (threadIdx.x == 0) {
     const unsigned int target = round * gridDim.x;
     unsigned int v;
@@ -98,7 +109,7 @@ __device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int round,
   }
   __syncthreads();
 }
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round, Prof& pf) {
+static __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round, Prof& pf) {
   long long t0 = 0;
   grid_arrive(bar, round, pf, t0);
   grid_wait(bar, round, pf, t0);
@@ -106,20 +117,20 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& round
 
 // 8 consecutive weights of a row as one lane's registers: bf16 = one 16-byte load, fp32 = two
 template <typename TW> struct W8 { uint4 q[sizeof(TW) / 2]; };
-template <typename TW> __device__ __forceinline__ void w8_load(W8<TW>& w, const TW* p) {
+template <typename TW> static __device__ __forceinline__ void w8_load(W8<TW>& w, const TW* p) {
 #pragma unroll
   for (int i = 0; i < (int)(sizeof(TW) / 2); ++i) w.q[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
 }
-template <typename TW> __device__ __forceinline__ void w8_zero(W8<TW>& w) {
+template <typename TW> static __device__ __forceinline__ void w8_zero(W8<TW>& w) {
 #pragma unroll
   for (int i = 0; i < (int)(sizeof(TW) / 2); ++i) w.q[i] = make_uint4(0u, 0u, 0u, 0u);
 }
-__device__ __forceinline__ void w8_unpack(const W8<bf16>& w, float (&f)[8]) {
+static __device__ __forceinline__ void w8_unpack(const W8<bf16>& w, float (&f)[8]) {
   const uint32_t u[4] = {w.q[0].x, w.q[0].y, w.q[0].z, w.q[0].w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(u[i] << 16); f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
 }
-__device__ __forceinline__ void w8_unpack(const W8<float>& w, float (&f)[8]) {
+static __device__ __forceinline__ void w8_unpack(const W8<float>& w, float (&f)[8]) {
   f[0] = __uint_as_float(w.q[0].x); f[1] = __uint_as_float(w.q[0].y); f[2] = __uint_as_float(w.q[0].z); f[3] = __uint_as_float(w.q[0].w);
   f[4] = __uint_as_float(w.q[1].x); f[5] = __uint_as_float(w.q[1].y); f[6] = __uint_as_float(w.q[1].z); f[7] = __uint_as_float(w.q[1].w);
 }
@@ -159,7 +170,7 @@ struct Pre { float b0, b1, o0, o1, sn, cs; float4 sc, pv; float* d0; float* d1; 
 
 // Work split of one GEMV phase: CTA c owns the output row PAIRS [c*P/G, (c+1)*P/G) (pair = rows 2p, 2p+1, or p, p+N for
 // GLU), cut along K into 256-column segments; a wave is PW pairs x KS segments <= WSEGS slots, slot s -> warp s % WPB.
-__device__ __forceinline__ Geo make_geo(const Phase& ph) {
+static __device__ __forceinline__ Geo make_geo(const Phase& ph) {
   const int npairs = ph.epi == EP_GLU ? ph.N : ph.N >> 1;
   Geo g;
   g.p_lo = (int)(blockIdx.x * (unsigned)npairs / gridDim.x);              // npairs <= 8192, grid <= a few hundred: 32 bits
@@ -173,7 +184,7 @@ __device__ __forceinline__ Geo make_geo(const Phase& ph) {
 // Issue the 16-byte loads of one wave's weights (no use of the data here: the caller may put a grid barrier and other
 // phases between this and the FMAs, so HBM / L2 latency overlaps the barrier).
 template <typename TW>
-__device__ __forceinline__ void load_wave(const Phase& ph, const Geo& g, int wave, WRegs<TW>& w) {
+static __device__ __forceinline__ void load_wave(const Phase& ph, const Geo& g, int wave, WRegs<TW>& w) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TW* W = reinterpret_cast<const TW*>(ph.wt);
   const int pbase = wave * g.PW;
@@ -198,7 +209,7 @@ __device__ __forceinline__ void load_wave(const Phase& ph, const Geo& g, int wav
 
 // everything of phase `ph` (pos filled in) that can be loaded before the barrier in front of it
 template <int BT, typename TW>
-__device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pre& pre) {
+static __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pre& pre) {
   const Geo& g = ph.g;
   load_wave<TW>(ph, g, 0, w);
   if constexpr (BT == 1) {
@@ -226,7 +237,7 @@ __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pr
   }
 }
 
-__device__ __forceinline__ float block_sum(float v, float* scratch /* [WPB] */) {
+static __device__ __forceinline__ float block_sum(float v, float* scratch /* [WPB] */) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
   __syncthreads();
@@ -238,13 +249,13 @@ __device__ __forceinline__ float block_sum(float v, float* scratch /* [WPB] */) 
 
 // shared-memory position of activation column k (k % 4 == 0) of a staged row.  B <= 8: the two 16-byte halves of every
 // 8-column group live in two planes, so the lanes of a warp (8 columns each) read consecutive 16-byte words.
-template <int BT> __device__ __forceinline__ int xs_off(int k) {
+template <int BT> static __device__ __forceinline__ int xs_off(int k) {
   if constexpr (Tile<BT>::LANEB) return k;
   else return ((k >> 2) & 1) * (Tile<BT>::KCB / 2) + (k >> 3) * 4;
 }
 
 // merged attention output of (sequence 0, columns k..k+3) from the per-slice partials (B = 1: the out-proj phase merges)
-__device__ __forceinline__ float4 merge_att(const Phase& ph, int k) {
+static __device__ __forceinline__ float4 merge_att(const Phase& ph, int k) {
   const int dh = ph.dim_head, w = ph.window;
   const int win = ph.pos / w, i = ph.pos % w;
   const int nreal = (win > 0 ? w : 0) + i + 1;
@@ -287,7 +298,7 @@ __device__ __forceinline__ float4 merge_att(const Phase& ph, int k) {
 // One GEMV / skinny-GEMM phase over all B sequences.  BT = compile-time batch tile (B <= BT).  `w`, `pre` hold what
 // prefetch_phase loaded for THIS phase (the caller ran it before the previous grid barrier, or just now).
 template <int BT, typename TW>
-__device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, float* part, float* stat, float* wsm, WRegs<TW>& w, const Pre& pre, const Prof& pf,
+static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, float* part, float* stat, float* wsm, WRegs<TW>& w, const Pre& pre, const Prof& pf,
                                            uint32_t sbar, uint32_t& sparity) {
   using TL = Tile<BT, sizeof(TW) == 2>;
   constexpr int KCB = TL::KCB, XP = TL::XP, BTP = TL::BTP;
@@ -333,6 +344,95 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
       }
     }
     if (in) *reinterpret_cast<float4*>(xs + xs_off<BT>(k)) = t;
+    __syncthreads();
+    staged = true;
+  } else if (LANEB && ph.pro == PRO_LN && nchunks == 1 && ph.K <= 512 && (ph.K & 127) == 0) {
+    // B > 8: the rows arrive by bulk copies (L2 -> shared memory at the L2 rate: every CTA reads the same 128 KB at the same
+    // time), the token-shift state of this warp's rows by register loads issued before the wait; then a warp per row normalises
+    // in place.  Instruction count matters here (64 rows per CTA): NJ = K / 128 is a compile-time constant, 1 / K a multiply.
+    constexpr int RPW = (BT + WPB - 1) / WPB;               // rows per warp
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(sbar, (uint32_t)(B * ph.K * 4));
+    if (threadIdx.x < B)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(xs + threadIdx.x * XP)), "l"(ph.xin + (long long)threadIdx.x * ph.ldx), "r"((uint32_t)(ph.K * 4)), "r"(sbar) : "memory");
+    float4 pvv[RPW][2];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int b = warp + rr * WPB;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = j * 128 + lane * 4;
+        pvv[rr][j] = (ph.ln_prev && b < B && k < half)
+                         ? __ldcg(reinterpret_cast<const float4*>(ph.ln_prev + (long long)b * ph.K + (ph.pos & 1) * half + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float inv_k = 1.f / (float)ph.K;
+    mbar_wait(sbar, sparity);
+    sparity ^= 1u;
+    prof_mark(pf, 7);
+    auto norm_rows = [&](auto nj_c) {
+      constexpr int NJ = decltype(nj_c)::value;
+      float4 sc[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) sc[j] = *reinterpret_cast<const float4*>(ph.ln_scale + j * 128 + lane * 4);
+#pragma unroll
+      for (int r0 = 0; r0 < RPW; r0 += 2) {
+        // two rows in flight per warp (their reductions are independent chains)
+        float4 v[2][NJ];
+        float mean[2], rstd[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int b = warp + (r0 + u) * WPB;
+          const float* xr = xs + (b < B ? b : 0) * XP + lane * 4;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) v[u][j] = *reinterpret_cast<const float4*>(xr + j * 128);
+        }
+        {
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) { sa += (v[0][j].x + v[0][j].y) + (v[0][j].z + v[0][j].w); sb += (v[1][j].x + v[1][j].y) + (v[1][j].z + v[1][j].w); }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, off); sb += __shfl_xor_sync(0xffffffffu, sb, off); }
+          mean[0] = sa * inv_k; mean[1] = sb * inv_k;
+          float qa = 0.f, qb = 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            v[0][j].x -= mean[0]; v[0][j].y -= mean[0]; v[0][j].z -= mean[0]; v[0][j].w -= mean[0];
+            v[1][j].x -= mean[1]; v[1][j].y -= mean[1]; v[1][j].z -= mean[1]; v[1][j].w -= mean[1];
+            qa = fmaf(v[0][j].x, v[0][j].x, fmaf(v[0][j].y, v[0][j].y, fmaf(v[0][j].z, v[0][j].z, fmaf(v[0][j].w, v[0][j].w, qa))));
+            qb = fmaf(v[1][j].x, v[1][j].x, fmaf(v[1][j].y, v[1][j].y, fmaf(v[1][j].z, v[1][j].z, fmaf(v[1][j].w, v[1][j].w, qb))));
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) { qa += __shfl_xor_sync(0xffffffffu, qa, off); qb += __shfl_xor_sync(0xffffffffu, qb, off); }
+          rstd[0] = rsqrtf(qa * inv_k + 1e-5f); rstd[1] = rsqrtf(qb * inv_k + 1e-5f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int rr = r0 + u;
+          const int b = warp + rr * WPB;
+          if (rr >= RPW || b >= B) continue;                 // warp-uniform
+          float* xr = xs + b * XP + lane * 4;
+          float* st = ph.ln_prev ? ph.ln_prev + (long long)b * ph.K + ((ph.pos + 1) & 1) * half + lane * 4 : nullptr;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            float4 t = make_float4(v[u][j].x * rstd[u] * sc[j].x, v[u][j].y * rstd[u] * sc[j].y, v[u][j].z * rstd[u] * sc[j].z, v[u][j].w * rstd[u] * sc[j].w);
+            if (st && j * 128 + lane * 4 < half) {           // (half = NJ * 64: j < NJ / 2, or the lower lanes of the middle j)
+              if (blockIdx.x == 0) *reinterpret_cast<float4*>(st + j * 128) = t;
+              t = pvv[rr < RPW ? rr : 0][j < 2 ? j : 0];
+            }
+            *reinterpret_cast<float4*>(xr + j * 128) = t;
+          }
+        }
+      }
+    };
+    switch (ph.K >> 7) {
+      case 1: norm_rows(std::integral_constant<int, 1>{}); break;
+      case 2: norm_rows(std::integral_constant<int, 2>{}); break;
+      case 3: norm_rows(std::integral_constant<int, 3>{}); break;
+      default: norm_rows(std::integral_constant<int, 4>{}); break;
+    }
     __syncthreads();
     staged = true;
   } else if (BT > 1 && ph.pro == PRO_LN && nchunks == 1 && ph.K <= 1024) {
@@ -393,8 +493,9 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
         }
       }
     };
-    if (ph.K <= 512) ln_rows(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
-    else ln_rows(std::integral_constant<int, 2>{}, std::integral_constant<int, 8>{});
+    constexpr int RFW = TPB > 256 ? 2 : 4;                 // (128 registers per thread with 16 warps)
+    if (ph.K <= 512) ln_rows(std::integral_constant<int, RFW>{}, std::integral_constant<int, 4>{});
+    else ln_rows(std::integral_constant<int, RFW / 2>{}, std::integral_constant<int, 8>{});
     __syncthreads();
     staged = true;
   } else if (ph.pro == PRO_LN) {
@@ -417,7 +518,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
     __syncthreads();
   }
   // stage x[:, k0 .. k0+kn) (with the prologue) into shared memory; U independent loads in flight per thread
-  constexpr int U = LANEB ? 16 : 4;
+  constexpr int U = LANEB ? 8 : 4;
   auto stage_regs = [&](int kc) {
     const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
     const int nvec = B * (kn >> 2);
@@ -652,96 +753,119 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
           if (nchunks > 1) { stage(kc); __syncthreads(); }
           const int k0 = kc * KCB, kn = min(KCB, ph.K - k0);
           const float* xa = xs + (mt * 16 + gr) * XP + gc;
+          // the k-loop is instantiated for 1, 2, 4 or 8 n-tiles: fragment loads and MMAs of absent tiles cost issue slots,
+          // and issue slots are what bounds this loop (the three-way split is ~50 instructions per k-step on its own)
+          auto mma_chunk = [&](auto ntc_c) {
+            constexpr int NTC = decltype(ntc_c)::value;
 #pragma unroll 2
-          for (int kb = kh * 16; kb < kn; kb += NKH * 16) {
-            uint32_t a1[4], a2[4], a3[4];
-            {
-              const float2 v0 = *reinterpret_cast<const float2*>(xa + kb);
-              const float2 v1 = *reinterpret_cast<const float2*>(xa + 8 * XP + kb);
-              const float2 v2 = *reinterpret_cast<const float2*>(xa + kb + 8);
-              const float2 v3 = *reinterpret_cast<const float2*>(xa + 8 * XP + kb + 8);
-              split3_bf16x2(v0.x, v0.y, a1[0], a2[0], a3[0]);
-              split3_bf16x2(v1.x, v1.y, a1[1], a2[1], a3[1]);
-              split3_bf16x2(v2.x, v2.y, a1[2], a2[2], a3[2]);
-              split3_bf16x2(v3.x, v3.y, a1[3], a2[3], a3[3]);
+            for (int kb = kh * 16; kb < kn; kb += NKH * 16) {
+              uint32_t a1[4], a2[4], a3[4];
+              {
+                const float2 v0 = *reinterpret_cast<const float2*>(xa + kb);
+                const float2 v1 = *reinterpret_cast<const float2*>(xa + 8 * XP + kb);
+                const float2 v2 = *reinterpret_cast<const float2*>(xa + kb + 8);
+                const float2 v3 = *reinterpret_cast<const float2*>(xa + 8 * XP + kb + 8);
+                split3_bf16x2(v0.x, v0.y, a1[0], a2[0], a3[0]);
+                split3_bf16x2(v1.x, v1.y, a1[1], a2[1], a3[1]);
+                split3_bf16x2(v2.x, v2.y, a1[2], a2[2], a3[2]);
+                split3_bf16x2(v3.x, v3.y, a1[3], a2[3], a3[3]);
+              }
+              const __nv_bfloat16* wk = wb + gr * WKP + k0 + kb + gc;
+              uint32_t fb0[NTC], fb1[NTC];
+#pragma unroll
+              for (int nt = 0; nt < NTC; ++nt) {
+                const int nn = nt < NT ? nt : 0;               // (NT <= NTC; clamped: unconditional loads inside the staged rows)
+                fb0[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP);
+                fb1[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP + 8);
+              }
+              // term-major, smallest terms first: consecutive MMAs hit different accumulators
+#pragma unroll
+              for (int nt = 0; nt < NTC; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a3, fb0[nt], fb1[nt]);
+#pragma unroll
+              for (int nt = 0; nt < NTC; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a2, fb0[nt], fb1[nt]);
+#pragma unroll
+              for (int nt = 0; nt < NTC; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a1, fb0[nt], fb1[nt]);
             }
-            const __nv_bfloat16* wk = wb + gr * WKP + k0 + kb + gc;
-            uint32_t fb0[NTMAX], fb1[NTMAX];
-#pragma unroll
-            for (int nt = 0; nt < NTMAX; ++nt) {
-              const int nn = nt < NT ? nt : 0;                 // (clamped: unconditional loads)
-              fb0[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP);
-              fb1[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP + 8);
-            }
-            // term-major, smallest terms first: consecutive MMAs hit different accumulators
-#pragma unroll
-            for (int nt = 0; nt < NTMAX; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a3, fb0[nt], fb1[nt]);
-#pragma unroll
-            for (int nt = 0; nt < NTMAX; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a2, fb0[nt], fb1[nt]);
-#pragma unroll
-            for (int nt = 0; nt < NTMAX; ++nt) if (nt < NT) mma_bf16_16816(acc[nt], a1, fb0[nt], fb1[nt]);
-          }
+          };
+          if (NT <= 1) mma_chunk(std::integral_constant<int, 1>{});
+          else if (NT <= 2) mma_chunk(std::integral_constant<int, 2>{});
+          else if (NT <= 4) mma_chunk(std::integral_constant<int, 4>{});
+          else mma_chunk(std::integral_constant<int, NTMAX>{});
         }
         prof_mark(pf, 6);
-        // (3) K splits 1.. -> shared memory, split 0 adds them in order, then the epilogue from its registers:
-        // lane holds (sequence gr | gr + 8 of the m-tile) x (weight rows 8 nt + gc, + 1 = the two rows of pair 4 nt + gc / 2)
-        if (kh > 0) {
+        // (3) the K splits are summed pairwise, halving round by round through shared memory (split q + h -> split q, a fixed
+        // order), then split 0 runs the epilogue from its registers: lane holds (sequence gr | gr + 8 of the m-tile) x (weight
+        // rows 8 nt + gc, + 1 = the two rows of pair 4 nt + gc / 2)
 #pragma unroll
-          for (int nt = 0; nt < NTMAX; ++nt)
-            if (nt < NT) *reinterpret_cast<float4*>(part + ((kh - 1) * NMT + mt) * 1024 + nt * 128 + lane * 4) =
-                make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
-        }
-        __syncthreads();
-        prof_mark(pf, 2);
-        if (kh == 0) {
-          // every operand of the epilogue first (bias, old residual values, rotary entries: independent loads), then the math
-          const int b0 = mt * 16 + gr;
-          float bia[NTMAX][2], old[NTMAX][4], rot[NTMAX][2];
+        for (int h = NKH / 2; h >= 1; h >>= 1) {
+          if (kh >= h && kh < 2 * h) {
 #pragma unroll
-          for (int nt = 0; nt < NTMAX; ++nt) {
-            const int pl = nt * 4 + (lane & 3);
-            const bool v = nt < NT && pl < pw;
-            const int pair = g.p_lo + pbase + (v ? pl : 0);
-            const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
-            bia[nt][0] = ph.bias ? ph.bias[r0] : 0.f;
-            bia[nt][1] = ph.bias ? ph.bias[r1] : 0.f;
-            old[nt][0] = old[nt][1] = old[nt][2] = old[nt][3] = 0.f;
-            if (ph.epi == EP_RESIDUAL) {
-              const float* o0 = ph.out + (long long)(b0 < B ? b0 : 0) * ph.ldo;
-              const float* o1 = ph.out + (long long)(b0 + 8 < B ? b0 + 8 : 0) * ph.ldo;
-              old[nt][0] = __ldcg(o0 + r0); old[nt][1] = __ldcg(o0 + r1);
-              old[nt][2] = __ldcg(o1 + r0); old[nt][3] = __ldcg(o1 + r1);
-            }
-            rot[nt][0] = rot[nt][1] = 0.f;
-            if (ph.epi == EP_ROTARY_CACHE) {
-              const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
-              rot[nt][0] = ph.rot_sin[ph.pos * hd + j]; rot[nt][1] = ph.rot_cos[ph.pos * hd + j];
-            }
+            for (int nt = 0; nt < NTMAX; ++nt)
+              if (nt < NT) *reinterpret_cast<float4*>(part + ((kh - h) * NMT + mt) * 1024 + nt * 128 + lane * 4) =
+                  make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
           }
+          __syncthreads();
+          if (kh < h) {
 #pragma unroll
-          for (int nt = 0; nt < NTMAX; ++nt) {
-            if (nt < NT) {
-#pragma unroll
-              for (int q = 1; q < NKH; ++q) {
-                const float4 v = *reinterpret_cast<const float4*>(part + ((q - 1) * NMT + mt) * 1024 + nt * 128 + lane * 4);
+            for (int nt = 0; nt < NTMAX; ++nt) {
+              if (nt < NT) {
+                const float4 v = *reinterpret_cast<const float4*>(part + (kh * NMT + mt) * 1024 + nt * 128 + lane * 4);
                 acc[nt][0] += v.x; acc[nt][1] += v.y; acc[nt][2] += v.z; acc[nt][3] += v.w;
               }
+            }
+          }
+          if (h > 1) __syncthreads();
+        }
+        prof_mark(pf, 2);
+        if (kh == 0) {
+          // two n-tiles at a time: every operand of their epilogues first (bias, old residual values, rotary entries:
+          // independent loads), then the math and the stores
+          const int b0 = mt * 16 + gr;
+#pragma unroll
+          for (int n0 = 0; n0 < NTMAX; n0 += 2) {
+            if (n0 >= NT) continue;                            // (no break: the loop must unroll, acc[] is indexed statically)
+            float bia[2][2], old[2][4], rot[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int nt = n0 + u;
               const int pl = nt * 4 + (lane & 3);
-              if (pl < pw) {
+              const bool v = nt < NT && pl < pw;
+              const int pair = g.p_lo + pbase + (v ? pl : 0);
+              const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+              bia[u][0] = ph.bias ? ph.bias[r0] : 0.f;
+              bia[u][1] = ph.bias ? ph.bias[r1] : 0.f;
+              old[u][0] = old[u][1] = old[u][2] = old[u][3] = 0.f;
+              if (ph.epi == EP_RESIDUAL) {
+                const float* o0 = ph.out + (long long)(b0 < B ? b0 : 0) * ph.ldo;
+                const float* o1 = ph.out + (long long)(b0 + 8 < B ? b0 + 8 : 0) * ph.ldo;
+                old[u][0] = __ldcg(o0 + r0); old[u][1] = __ldcg(o0 + r1);
+                old[u][2] = __ldcg(o1 + r0); old[u][3] = __ldcg(o1 + r1);
+              }
+              rot[u][0] = rot[u][1] = 0.f;
+              if (ph.epi == EP_ROTARY_CACHE) {
+                const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
+                rot[u][0] = ph.rot_sin[ph.pos * hd + j]; rot[u][1] = ph.rot_cos[ph.pos * hd + j];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int nt = n0 + u;
+              const int pl = nt * 4 + (lane & 3);
+              if (nt < NT && pl < pw) {
                 const int pair = g.p_lo + pbase + pl;
                 const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
                   const int b = b0 + 8 * hb;
                   if (b >= B) continue;
-                  const float s0 = acc[nt][2 * hb] + bia[nt][0], s1 = acc[nt][2 * hb + 1] + bia[nt][1];
+                  const float s0 = acc[nt][2 * hb] + bia[u][0], s1 = acc[nt][2 * hb + 1] + bia[u][1];
                   float* o = ph.out + (long long)b * ph.ldo;
                   if (ph.epi == EP_BIAS) { o[r0] = s0; o[r1] = s1; }
-                  else if (ph.epi == EP_RESIDUAL) { o[r0] = old[nt][2 * hb] + s0; o[r1] = old[nt][2 * hb + 1] + s1; }
+                  else if (ph.epi == EP_RESIDUAL) { o[r0] = old[u][2 * hb] + s0; o[r1] = old[u][2 * hb + 1] + s1; }
                   else if (ph.epi == EP_GELU) { o[r0] = gelu_tanh(s0); o[r1] = gelu_tanh(s1); }
                   else if (ph.epi == EP_GLU) { o[r0] = s0 * gelu_tanh(s1); }
                   else {
-                    const float sn = rot[nt][0], cs = rot[nt][1];
+                    const float sn = rot[u][0], cs = rot[u][1];
                     const int sec = r0 / ph.inner, c = r0 % ph.inner;
                     float* dst = sec == 0 ? o + c : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)b * ph.n + ph.pos) * ph.inner + c;
                     dst[0] = s0 * cs - s1 * sn; dst[1] = s1 * cs + s0 * sn;
@@ -830,7 +954,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, fl
 // merges the partials (plus window 0's w zero keys with logit 0, quirk Q1) into att[b, head * dh ..]; B = 1: the out-proj
 // phase merges while it stages its input (merge_att).
 template <bool MERGE, int NL /* lanes that cover one value row with float4 = dim_head / 4 */>
-__device__ void attention_phase_t(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq /* smem [WPB][dh] */) {
+static __device__ void attention_phase_t(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq /* smem [WPB][dh] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = r.dim_head, w = r.window, I = r.inner;
   const int win = pos / w, i = pos % w;
@@ -938,23 +1062,27 @@ __device__ void attention_phase_t(const progen_decode_run_t& r, const float* kca
   }
 }
 
-// B > 1: WP warps (1, 2, 4 or 8, all of one CTA) own one (sequence, head): each walks its share of the 32-key slices with a
+// B > 1: WP warps (1, 2, 4 or 8, all of one CTA) own one (sequence, head): each walks its share of the 16-key slices with a
 // running (max, sum, out) and the WP partials are merged through shared memory — no global partials, no atomics, no fences.
+// Two lanes per key for the logits (half a key row each: 32 registers at dim_head 64), lane = (key group, 4 channels) for
+// the value sum; every load of a slice is independent of the others.
 template <int NL>
-__device__ void attention_batch_t(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq /* smem >= WPB * (dh + 4) + WPB * dh */) {
+static __device__ void attention_batch_t(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq /* smem >= WPB * (2 dh + 4) */) {
+  static_assert(NL >= 2, "two lanes share a key row");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int dh = NL * 4, KG = 32 / NL, NH = NL >= 2 ? NL / 2 : 1;
+  constexpr int dh = NL * 4, HK = NL / 2, KG = 32 / NL, NV = 16 / KG;
   const int w = r.window, I = r.inner;
   const int win = pos / w, i = pos % w;
   const int key0 = win > 0 ? (win - 1) * w : 0;
   const int nreal = (win > 0 ? w : 0) + i + 1;
-  const int nsl = (nreal + 31) / 32;
+  const int nsl = (nreal + 15) / 16;
   const int npairs = r.B * r.heads;
   int WP = 8;
   while (WP > 1 && (long long)npairs * WP > (long long)gridDim.x * WPB) WP >>= 1;
   const int slots = WPB / WP, slot = warp / WP, sub = warp % WP;
   const int rounds = (npairs + gridDim.x * slots - 1) / (gridDim.x * slots);
   const float scale = rsqrtf((float)dh);
+  const int key_l = lane >> 1, hf = lane & 1;
   const int kg = lane / NL, c4 = (lane % NL) * 4;
   float* q_s = sq + warp * dh;                                // this warp's copy of q
   float* mrg = sq + WPB * dh;                                 // [WPB][dh + 4] partials
@@ -968,45 +1096,40 @@ __device__ void attention_batch_t(const progen_decode_run_t& r, const float* kca
       const float* qv = r.q + (long long)b * I + hh * dh;
       if (lane < NL) *reinterpret_cast<float4*>(q_s + lane * 4) = __ldcg(reinterpret_cast<const float4*>(qv + lane * 4));
       __syncwarp();
+      const float* kbase = kcache + ((long long)b * r.n + key0) * I + hh * dh + hf * 4;     // lane hf takes float4s hf, hf + 2, ...:
+                                                                                          // the pair reads one whole 32-byte sector per load
+      const float* vbase = vcache + ((long long)b * r.n + key0) * I + hh * dh + c4;
       for (int sl = sub; sl < nsl; sl += WP) {
-        const int j = sl * 32 + lane;
+        const int j = sl * 16 + key_l;
         const bool valid = j < nreal;
-        const int nk = min(32, nreal - sl * 32);
-        const float* kr = kcache + ((long long)b * r.n + key0 + (valid ? j : 0)) * I + hh * dh;
-        const float* vb = vcache + ((long long)b * r.n + key0 + sl * 32) * I + hh * dh + c4;
-        float4 kreg[NL], vreg[NH];
+        const int nk = min(16, nreal - sl * 16);
+        const float* kr = kbase + (long long)(valid ? j : 0) * I;
+        float4 kreg[HK], vreg[NV];
 #pragma unroll
-        for (int c = 0; c < NL; ++c) kreg[c] = __ldcg(reinterpret_cast<const float4*>(kr + c * 4));
+        for (int c = 0; c < HK; ++c) kreg[c] = __ldcg(reinterpret_cast<const float4*>(kr + c * 8));
 #pragma unroll
-        for (int jj = 0; jj < NH; ++jj) {
+        for (int jj = 0; jj < NV; ++jj) {
           const int key = kg + jj * KG;
-          vreg[jj] = key < nk ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vreg[jj] = key < nk ? __ldcg(reinterpret_cast<const float4*>(vbase + (long long)(sl * 16 + key) * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < NL; ++c) {
-          const float4 qq = *reinterpret_cast<const float4*>(q_s + c * 4);
+        for (int c = 0; c < HK; ++c) {
+          const float4 qq = *reinterpret_cast<const float4*>(q_s + hf * 4 + c * 8);
           s = fmaf(kreg[c].x, qq.x, s); s = fmaf(kreg[c].y, qq.y, s); s = fmaf(kreg[c].z, qq.z, s); s = fmaf(kreg[c].w, qq.w, s);
         }
-        float4 vreg2[NH];
-#pragma unroll
-        for (int jj = 0; jj < NH; ++jj) {
-          const int key = kg + (jj + NH) * KG;
-          vreg2[jj] = (NH + jj < NL && key < nk) ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
         s = valid ? s * scale : -INFINITY;
         const float mn = fmaxf(m, warp_max(s));               // finite: every slice has at least one real key
         const float f = expf(m - mn);                          // 0 for the first slice (m = -inf)
         const float pv = valid ? expf(s - mn) : 0.f;
-        lsum = lsum * f + pv;
+        lsum = lsum * f + (hf == 0 ? pv : 0.f);                // each key once
         o.x *= f; o.y *= f; o.z *= f; o.w *= f;
         m = mn;
 #pragma unroll
-        for (int jj = 0; jj < NL; ++jj) {
-          const int key = kg + jj * KG;
-          const float pj = __shfl_sync(0xffffffffu, pv, key & 31);
-          const float4 vv = jj < NH ? vreg[jj % NH] : vreg2[jj % NH];
-          o.x = fmaf(pj, vv.x, o.x); o.y = fmaf(pj, vv.y, o.y); o.z = fmaf(pj, vv.z, o.z); o.w = fmaf(pj, vv.w, o.w);
+        for (int jj = 0; jj < NV; ++jj) {
+          const float pj = __shfl_sync(0xffffffffu, pv, (2 * (kg + jj * KG)) & 31);
+          o.x = fmaf(pj, vreg[jj].x, o.x); o.y = fmaf(pj, vreg[jj].y, o.y); o.z = fmaf(pj, vreg[jj].z, o.z); o.w = fmaf(pj, vreg[jj].w, o.w);
         }
       }
       for (int off = NL; off < 32; off <<= 1) {
@@ -1039,18 +1162,17 @@ __device__ void attention_batch_t(const progen_decode_run_t& r, const float* kca
     __syncthreads();
   }
 }
-__device__ void attention_batch(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq) {
+static __device__ void attention_batch(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq) {
   switch (r.dim_head) {
     case 64: attention_batch_t<16>(r, kcache, vcache, pos, sq); break;
     case 32: attention_batch_t<8>(r, kcache, vcache, pos, sq); break;
     case 16: attention_batch_t<4>(r, kcache, vcache, pos, sq); break;
-    case 8: attention_batch_t<2>(r, kcache, vcache, pos, sq); break;
-    default: attention_batch_t<1>(r, kcache, vcache, pos, sq); break;
+    default: attention_batch_t<2>(r, kcache, vcache, pos, sq); break;
   }
 }
 
 template <bool MERGE>
-__device__ void attention_phase(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq) {
+static __device__ void attention_phase(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq) {
   switch (r.dim_head) {
     case 64: attention_phase_t<MERGE, 16>(r, kcache, vcache, pos, sq); break;
     case 32: attention_phase_t<MERGE, 8>(r, kcache, vcache, pos, sq); break;
@@ -1066,12 +1188,12 @@ __device__ void attention_phase(const progen_decode_run_t& r, const float* kcach
 // partial gate' goes to sg[split][b][c] (split 0 adds the current position's term and the bias); the SGU projection
 // phase multiplies xs with the sum of the partials while it stages its input (PRO_SGU).
 struct SguArgs { const float* ln_scale; const float* w; const float* b; float* hist; };
-__device__ __forceinline__ int sgu_splits(const progen_decode_run_t& r) {
+static __device__ __forceinline__ int sgu_splits(const progen_decode_run_t& r) {
   const int base = r.B * (r.hid / 2 / 128);
   int s = (int)gridDim.x / (base > 0 ? base : 1);
   return s < 1 ? 1 : (s > MAXSPLIT ? MAXSPLIT : s);
 }
-__device__ void sgu_phase(const progen_decode_run_t& r, const SguArgs& L, int pos, float* red /* smem [WPB][128] + stats */) {
+static __device__ void sgu_phase(const progen_decode_run_t& r, const SguArgs& L, int pos, float* red /* smem [WPB][128] + stats */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = r.hid / 2, n = r.n;
   const int cblocks = C / 128;
@@ -1156,7 +1278,7 @@ __device__ void sgu_phase(const progen_decode_run_t& r, const SguArgs& L, int po
 // ------------------------------------------------------------------------------------------------ sampler (one sequence per CTA)
 // utils.py:97-129: top-k filter keeps logits > (k-th largest), the rest become 0.0 and lose their noise; argmax(logits +
 // gumbel) (first maximal index); seq[pos + 1] += index (ADD, quirk Q5).  Then the next position's embedding row.
-__device__ void sample_phase(const progen_decode_run_t& r, int pos, float* sv /* smem [V] */, float* red) {
+static __device__ void sample_phase(const progen_decode_run_t& r, int pos, float* sv /* smem [V] */, float* red) {
   const int t = threadIdx.x, V = r.V, lane = t & 31, warp = t >> 5;
   int* redi = reinterpret_cast<int*>(red + 32);
   for (int b = blockIdx.x; b < r.B; b += gridDim.x) {
@@ -1228,11 +1350,11 @@ __device__ void sample_phase(const progen_decode_run_t& r, int pos, float* sv /*
 
 enum { K_NONE = 0, K_GEMV = 1, K_ATT = 2, K_SGU = 3, K_SAMPLE = 4 };
 struct PhaseEnt { int kind, next; Phase ph; };     // next: table index of the following GEMV phase (weights to prefetch)
-__host__ __device__ inline int num_phases(int depth) { return depth * 7 + 2; }
+static __host__ __device__ int num_phases(int depth) { return depth * 7 + 2; }
 
 // Phase table (shared memory, built once per launch): per layer QKV | attention | out-proj | FF-in | [SGU | SGU proj] | FF-out,
 // then final LN + head, sampler.  Position-dependent fields (pos) are filled in at use.
-__device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, bool att_consumer_merge, int nsplit) {
+static __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, bool att_consumer_merge, int nsplit) {
   const int d = r.d, I = r.inner, hid = r.hid;
   const int nph = num_phases(r.depth);
   for (int li = threadIdx.x; li < r.depth; li += TPB) {
@@ -1290,13 +1412,13 @@ __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt* tab, b
   __syncthreads();
 }
 
-template <int BT, bool TCW> constexpr size_t decode_smem_floats() {
+template <int BT, bool TCW> static constexpr size_t decode_smem_floats() {
   using TL = Tile<BT, TCW>;
   return (size_t)BT * TL::XP + TL::PART + TL::STATF + TL::WSM + WPB * 128 + 64;
 }
 
 template <int BT, typename TW>
-__global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_decode_run_t r) {
+static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
   extern __shared__ __align__(16) float smem[];
   using TL = Tile<BT, sizeof(TW) == 2>;
   float* xs = smem;                                    // [BT][XP]
@@ -1371,11 +1493,20 @@ __global__ void __launch_bounds__(TPB, 1) decode_persistent_kernel(const progen_
   }
 }
 
+};  // struct Impl
+
+template <int BT, typename TW>
+__global__ void __launch_bounds__(threads_for(BT), 1) decode_persistent_kernel(const progen_decode_run_t r) {
+  Impl<threads_for(BT)>::template run<BT, TW>(r);
+}
+
 template <int BT, typename TW>
 int launch_run(const progen_decode_run_t& r, cudaStream_t s) {
-  using TL = Tile<BT, sizeof(TW) == 2>;
+  using IM = Impl<threads_for(BT)>;
+  using TL = typename IM::template Tile<BT, sizeof(TW) == 2>;
+  constexpr int TPB = threads_for(BT);
   static_assert((BT * TL::XP) % 4 == 0 && TL::PART % 4 == 0 && TL::WSM % 4 == 0, "the scratch regions must stay 16-byte aligned");
-  const size_t smem = decode_smem_floats<BT, sizeof(TW) == 2>() * sizeof(float) + (size_t)num_phases(r.depth) * sizeof(PhaseEnt);
+  const size_t smem = IM::template decode_smem_floats<BT, sizeof(TW) == 2>() * sizeof(float) + (size_t)IM::num_phases(r.depth) * sizeof(typename IM::PhaseEnt);
   PG_CHECK_ARG(smem <= 227 * 1024);
   auto kern = decode_persistent_kernel<BT, TW>;
   static size_t set_for = 0;
@@ -1403,7 +1534,7 @@ int progen_decode_run(const progen_decode_run_t* r, void* stream) {
   PG_CHECK_ARG(r != nullptr && r->layers != nullptr && r->depth > 0 && r->B >= 1 && r->B <= 64 && r->nsteps >= 0);
   PG_CHECK_ARG(r->d % 8 == 0 && r->inner % 8 == 0 && r->hid % 256 == 0 && r->V % 2 == 0 && r->V <= 512);
   PG_CHECK_ARG(r->d <= 8192 && r->inner <= 8192 && r->hid <= 8192);   // K segments of one pair fit a wave (KS <= WSEGS)
-  PG_CHECK_ARG(r->dim_head >= 4 && r->dim_head <= 64 && (r->dim_head & (r->dim_head - 1)) == 0);   // float4 lanes per value row
+  PG_CHECK_ARG(r->dim_head >= 8 && r->dim_head <= 64 && (r->dim_head & (r->dim_head - 1)) == 0);   // float4 lanes per value row
   PG_CHECK_ARG(r->window >= 1 && r->window <= 512);                    // <= 32 key slices per (sequence, head)
   PG_CHECK_ARG(r->pos0 >= 0 && r->pos0 + r->nsteps <= r->n);
   PG_CHECK_ARG(r->grid_bar != nullptr && r->att_count != nullptr && r->att_part != nullptr);

@@ -125,6 +125,28 @@ def test_batched_logits_match_oracle_forward(B, wdt):
         assert np.abs(got[b, :n - 1] - ref[:n - 1]).max() < 3e-5 * max(1.0, np.abs(ref).max()), b
 
 
+@pytest.mark.parametrize('B', [12, 40])
+def test_batched_tensor_pipe_path_at_model_width_512(B):
+    """config-1 width (d = 512, K = 512 / 2048 phases: bulk-copied LayerNorm rows, multi-chunk FF-out, 1-4 n-tiles per CTA) with
+    bf16 weights: B sequences on the tensor-pipe path == the same primes decoded alone (single-stream fp32 FMA path, same bf16
+    weights) — greedy ids equal, logits within fp32 round-off"""
+    import torch
+    from progen_b200.decode import BatchDecoder
+    cfg, params, data, g = load_case('cfg1')
+    rng = np.random.default_rng(B)
+    primes = [rng.integers(1, 256, int(rng.integers(2, 12))).astype(np.int64) for _ in range(B)]
+    many = BatchDecoder(cfg, params, batch=B, weights_dtype=torch.bfloat16, keep_logits=True)
+    ids, gen, secs = many.sample(primes, top_k=25, add_bos=True, greedy=True)
+    got = many.logits_all.cpu().numpy()
+    one = BatchDecoder(cfg, params, batch=1, weights_dtype=torch.bfloat16, keep_logits=True)
+    n = cfg['seq_len']
+    for b in (0, B // 3, B - 1):
+        ref_ids, _, _ = one.sample(primes[b], top_k=25, add_bos=True, greedy=True)
+        ref = one.logits_all.cpu().numpy()[0]
+        np.testing.assert_array_equal(ids[b], ref_ids)
+        assert np.abs(got[b, :n - 1] - ref[:n - 1]).max() < 5e-5 * max(1.0, np.abs(ref).max()), b
+
+
 @pytest.mark.parametrize('B', [3, 8, 33])
 def test_batched_decode_equals_single_stream(B):
     """B primes of different lengths decoded in lock step == each prime decoded alone (greedy, bit-equal ids)"""
