@@ -199,7 +199,8 @@ int progen_decode_step(const progen_decode_t* model, int do_sample, void* stream
 /* Whole-generation decode in ONE persistent cooperative kernel (csrc/decode_persist.cu): consumes positions
  * pos0 .. pos0 + nsteps - 1 of B sequences in lock step (reference utils.py:106-135 per sequence; sample.py:66-71).
  * `layers` is a DEVICE array of `depth` progen_decode_layer_t whose cache / state pointers are batch-major:
- * kcache, vcache [B, n, inner]; shift1, shift2 [B, 2, d/2]; gn_hist [B, n, hid/2].  Sequence b keeps its prime before
+ * kcache, vcache [B, heads, n, dim_head] (a head's keys are contiguous: the windowed read streams); shift1, shift2 [B, 2, d/2];
+ * gn_hist [B, n, hid/2].  Sequence b keeps its prime before
  * start[b]: position p+1 is sampled (seq[b][p+1] += id, quirk Q5) iff p+1 >= start[b].  grid_bar (one uint32) and att_count
  * ([B * heads] int32) must be zero on entry.  B <= 64. */
 typedef struct progen_decode_run_t {

@@ -225,7 +225,7 @@ static __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>
         const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
         pre.sn = ph.rot_sin[ph.pos * hd + j]; pre.cs = ph.rot_cos[ph.pos * hd + j];
         const int sec = r0 / ph.inner, c = r0 % ph.inner;
-        pre.d0 = sec == 0 ? ph.out + c : (sec == 1 ? ph.kcache : ph.vcache) + (long long)ph.pos * ph.inner + c;
+        pre.d0 = sec == 0 ? ph.out + c : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)(c / ph.dim_head) * ph.n + ph.pos) * ph.dim_head + c % ph.dim_head;
         pre.d1 = pre.d0 + 1;
       }
     }
@@ -618,7 +618,7 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
       const float o0 = s0 * cs - s1 * sn, o1 = s1 * cs + s0 * sn;
       const int sec = r0 / ph.inner, c = r0 % ph.inner;
       float* dst = sec == 0 ? o + c
-                            : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)b * ph.n + ph.pos) * ph.inner + c;
+                            : (sec == 1 ? ph.kcache : ph.vcache) + (((long long)b * (ph.inner / ph.dim_head) + c / ph.dim_head) * ph.n + ph.pos) * ph.dim_head + c % ph.dim_head;
       dst[0] = o0; dst[1] = o1;
     }
   };
@@ -867,7 +867,7 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
                   else {
                     const float sn = rot[u][0], cs = rot[u][1];
                     const int sec = r0 / ph.inner, c = r0 % ph.inner;
-                    float* dst = sec == 0 ? o + c : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)b * ph.n + ph.pos) * ph.inner + c;
+                    float* dst = sec == 0 ? o + c : (sec == 1 ? ph.kcache : ph.vcache) + (((long long)b * (ph.inner / ph.dim_head) + c / ph.dim_head) * ph.n + ph.pos) * ph.dim_head + c % ph.dim_head;
                     dst[0] = s0 * cs - s1 * sn; dst[1] = s1 * cs + s0 * sn;
                   }
                 }
@@ -950,10 +950,9 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
 // ------------------------------------------------------------------------------------------------ attention
 // task = (sequence, head, slice of 32 keys), one warp: partial (m, l, o[dh]) -> att_part[(b, head)][slice][dh + 4].  All of
 // the task's K and V loads are independent of each other (lane = key for the logits; lane = (key group, 4 channels) for
-// the value sum), so a task is ONE memory round trip.  MERGE (B > 1): the warp that finishes a (sequence, head)'s last slice
-// merges the partials (plus window 0's w zero keys with logit 0, quirk Q1) into att[b, head * dh ..]; B = 1: the out-proj
-// phase merges while it stages its input (merge_att).
-template <bool MERGE, int NL /* lanes that cover one value row with float4 = dim_head / 4 */>
+// the value sum), so a task is ONE memory round trip.  The out-proj phase merges the partials (plus window 0's w zero keys
+// with logit 0, quirk Q1) while it stages its input (merge_att).  Single sequence only; B > 1 uses attention_batch.
+template <int NL /* lanes that cover one value row with float4 = dim_head / 4 */>
 static __device__ void attention_phase_t(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq /* smem [WPB][dh] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = r.dim_head, w = r.window, I = r.inner;
@@ -977,8 +976,8 @@ static __device__ void attention_phase_t(const progen_decode_run_t& r, const flo
     const int j = sl * 32 + lane;
     const bool valid = j < nreal;
     const int nk = min(32, nreal - sl * 32);
-    const float* kr = kcache + ((long long)b * r.n + key0 + (valid ? j : 0)) * I + hh * dh;
-    const float* vb = vcache + ((long long)b * r.n + key0 + sl * 32) * I + hh * dh + c4;
+    const float* kr = kcache + (((long long)b * r.heads + hh) * r.n + key0 + (valid ? j : 0)) * dh;      // caches: [B][heads][n][dh]
+    const float* vb = vcache + (((long long)b * r.heads + hh) * r.n + key0 + sl * 32) * dh + c4;
     // issue: the float4s of this lane's key row and the first half of this lane's value quads (keys kg, kg + KG, ...);
     // the second half goes out as soon as the key registers are consumed
     float4 kreg[NL], vreg[NH];
@@ -987,7 +986,7 @@ static __device__ void attention_phase_t(const progen_decode_run_t& r, const flo
 #pragma unroll
     for (int jj = 0; jj < NH; ++jj) {
       const int key = kg + jj * KG;
-      vreg[jj] = key < nk ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vreg[jj] = key < nk ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * dh)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
     float s = 0.f;
@@ -1000,7 +999,7 @@ static __device__ void attention_phase_t(const progen_decode_run_t& r, const flo
 #pragma unroll
     for (int jj = 0; jj < NH; ++jj) {
       const int key = kg + (jj + NH) * KG;
-      vreg2[jj] = (NH + jj < NL && key < nk) ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vreg2[jj] = (NH + jj < NL && key < nk) ? __ldcg(reinterpret_cast<const float4*>(vb + (long long)key * dh)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     s = valid ? s * scale : -INFINITY;
     const float m = warp_max(s);
@@ -1021,44 +1020,6 @@ static __device__ void attention_phase_t(const progen_decode_run_t& r, const flo
     float* pt = r.att_part + ((long long)bh * KS + sl) * PS;
     if (lane < NL) *reinterpret_cast<float4*>(pt + 4 + lane * 4) = o;
     if (lane == 0) *reinterpret_cast<float2*>(pt) = make_float2(m, l);
-    if constexpr (MERGE) {
-      // last slice of this (b, head) to finish merges: lane = slice for the weights, lane = (slice group, 4 channels) for o
-      __threadfence();
-      __syncwarp();
-      int last = 0;
-      if (lane == 0) last = atomicAdd(r.att_count + bh, 1) == nsl - 1;
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        __threadfence();
-        const float* pb = r.att_part + (long long)bh * KS * PS;
-        float4 oreg[NL];
-#pragma unroll
-        for (int jj = 0; jj < NL; ++jj) {
-          const int sx = kg + jj * KG;
-          oreg[jj] = sx < nsl ? __ldcg(reinterpret_cast<const float4*>(pb + sx * PS + 4 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float2 ml = lane < nsl ? __ldcg(reinterpret_cast<const float2*>(pb + lane * PS)) : make_float2(-INFINITY, 0.f);
-        float M = warp_max(ml.x);
-        if (win == 0) M = fmaxf(M, 0.f);                     // zero look-back keys of window 0: logit 0 (quirk Q1)
-        const float f = lane < nsl ? expf(ml.x - M) : 0.f;
-        float Lt = warp_sum(ml.y * f);
-        if (win == 0) Lt += (float)w * expf(-M);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int jj = 0; jj < NL; ++jj) {
-          const int sx = kg + jj * KG;
-          const float fs = __shfl_sync(0xffffffffu, f, sx & 31);               // f = 0 for slices that do not exist
-          a.x = fmaf(fs, oreg[jj].x, a.x); a.y = fmaf(fs, oreg[jj].y, a.y); a.z = fmaf(fs, oreg[jj].z, a.z); a.w = fmaf(fs, oreg[jj].w, a.w);
-        }
-        for (int off = NL; off < 32; off <<= 1) {
-          a.x += __shfl_xor_sync(0xffffffffu, a.x, off); a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
-          a.z += __shfl_xor_sync(0xffffffffu, a.z, off); a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
-        }
-        const float inv = 1.f / Lt;
-        if (lane < NL) *reinterpret_cast<float4*>(r.att + (long long)b * I + hh * dh + lane * 4) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
-        if (lane == 0) r.att_count[bh] = 0;
-      }
-    }
   }
 }
 
@@ -1096,22 +1057,24 @@ static __device__ void attention_batch_t(const progen_decode_run_t& r, const flo
       const float* qv = r.q + (long long)b * I + hh * dh;
       if (lane < NL) *reinterpret_cast<float4*>(q_s + lane * 4) = __ldcg(reinterpret_cast<const float4*>(qv + lane * 4));
       __syncwarp();
-      const float* kbase = kcache + ((long long)b * r.n + key0) * I + hh * dh + hf * 4;     // lane hf takes float4s hf, hf + 2, ...:
+      const float* kbase = kcache + (((long long)b * r.heads + hh) * r.n + key0) * dh + hf * 4;   // lane hf takes float4s hf, hf + 2, ...:
                                                                                           // the pair reads one whole 32-byte sector per load
-      const float* vbase = vcache + ((long long)b * r.n + key0) * I + hh * dh + c4;
-      for (int sl = sub; sl < nsl; sl += WP) {
+      const float* vbase = vcache + (((long long)b * r.heads + hh) * r.n + key0) * dh + c4;
+      // two slices per iteration: all their loads are issued before the first use (one memory round trip for 32 keys), one
+      // running-max update for both; a missing second slice re-reads the first with weight 0
+      auto load_slice = [&](int sl, float4 (&kreg)[HK], float4 (&vreg)[NV]) {
         const int j = sl * 16 + key_l;
-        const bool valid = j < nreal;
         const int nk = min(16, nreal - sl * 16);
-        const float* kr = kbase + (long long)(valid ? j : 0) * I;
-        float4 kreg[HK], vreg[NV];
+        const float* kr = kbase + (long long)(j < nreal ? j : 0) * dh;
 #pragma unroll
         for (int c = 0; c < HK; ++c) kreg[c] = __ldcg(reinterpret_cast<const float4*>(kr + c * 8));
 #pragma unroll
         for (int jj = 0; jj < NV; ++jj) {
           const int key = kg + jj * KG;
-          vreg[jj] = key < nk ? __ldcg(reinterpret_cast<const float4*>(vbase + (long long)(sl * 16 + key) * I)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vreg[jj] = __ldcg(reinterpret_cast<const float4*>(vbase + (long long)(sl * 16 + (key < nk ? key : 0)) * dh));
         }
+      };
+      auto logit = [&](int sl, const float4 (&kreg)[HK], bool on2) {
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < HK; ++c) {
@@ -1119,17 +1082,27 @@ static __device__ void attention_batch_t(const progen_decode_run_t& r, const flo
           s = fmaf(kreg[c].x, qq.x, s); s = fmaf(kreg[c].y, qq.y, s); s = fmaf(kreg[c].z, qq.z, s); s = fmaf(kreg[c].w, qq.w, s);
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s = valid ? s * scale : -INFINITY;
-        const float mn = fmaxf(m, warp_max(s));               // finite: every slice has at least one real key
-        const float f = expf(m - mn);                          // 0 for the first slice (m = -inf)
-        const float pv = valid ? expf(s - mn) : 0.f;
-        lsum = lsum * f + (hf == 0 ? pv : 0.f);                // each key once
+        return (on2 && sl * 16 + key_l < nreal) ? s * scale : -INFINITY;
+      };
+      for (int sl = sub; sl < nsl; sl += 2 * WP) {
+        const bool two = sl + WP < nsl;
+        const int slb = two ? sl + WP : sl;
+        float4 ka[HK], va[NV], kb[HK], vb[NV];
+        load_slice(sl, ka, va);
+        load_slice(slb, kb, vb);
+        const float sa = logit(sl, ka, true), sb = logit(slb, kb, two);
+        const float mn = fmaxf(m, warp_max(fmaxf(sa, sb)));   // finite: the first slice has at least one real key
+        const float f = expf(m - mn);                          // 0 for the first iteration (m = -inf)
+        const float pa = expf(sa - mn), pb = expf(sb - mn);    // exp(-inf) = 0 for masked keys
+        lsum = lsum * f + (hf == 0 ? pa + pb : 0.f);           // each key once
         o.x *= f; o.y *= f; o.z *= f; o.w *= f;
         m = mn;
 #pragma unroll
         for (int jj = 0; jj < NV; ++jj) {
-          const float pj = __shfl_sync(0xffffffffu, pv, (2 * (kg + jj * KG)) & 31);
-          o.x = fmaf(pj, vreg[jj].x, o.x); o.y = fmaf(pj, vreg[jj].y, o.y); o.z = fmaf(pj, vreg[jj].z, o.z); o.w = fmaf(pj, vreg[jj].w, o.w);
+          const int src = (2 * (kg + jj * KG)) & 31;           // (keys past the slice's end carry weight 0; their value row was clamped)
+          const float ja = __shfl_sync(0xffffffffu, pa, src), jb = __shfl_sync(0xffffffffu, pb, src);
+          o.x = fmaf(ja, va[jj].x, fmaf(jb, vb[jj].x, o.x)); o.y = fmaf(ja, va[jj].y, fmaf(jb, vb[jj].y, o.y));
+          o.z = fmaf(ja, va[jj].z, fmaf(jb, vb[jj].z, o.z)); o.w = fmaf(ja, va[jj].w, fmaf(jb, vb[jj].w, o.w));
         }
       }
       for (int off = NL; off < 32; off <<= 1) {
@@ -1171,14 +1144,12 @@ static __device__ void attention_batch(const progen_decode_run_t& r, const float
   }
 }
 
-template <bool MERGE>
 static __device__ void attention_phase(const progen_decode_run_t& r, const float* kcache, const float* vcache, int pos, float* sq) {
   switch (r.dim_head) {
-    case 64: attention_phase_t<MERGE, 16>(r, kcache, vcache, pos, sq); break;
-    case 32: attention_phase_t<MERGE, 8>(r, kcache, vcache, pos, sq); break;
-    case 16: attention_phase_t<MERGE, 4>(r, kcache, vcache, pos, sq); break;
-    case 8: attention_phase_t<MERGE, 2>(r, kcache, vcache, pos, sq); break;
-    default: attention_phase_t<MERGE, 1>(r, kcache, vcache, pos, sq); break;
+    case 64: attention_phase_t<16>(r, kcache, vcache, pos, sq); break;
+    case 32: attention_phase_t<8>(r, kcache, vcache, pos, sq); break;
+    case 16: attention_phase_t<4>(r, kcache, vcache, pos, sq); break;
+    default: attention_phase_t<2>(r, kcache, vcache, pos, sq); break;
   }
 }
 
@@ -1471,7 +1442,7 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
         have = fetch_next = !(e == nph - 2 && step + 1 == r.nsteps);
       } else if (kind == K_ATT) {
         if (MERGE_IN_ATT || !att_consumer) attention_batch(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
-        else attention_phase<false>(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
+        else attention_phase(r, tab[e].ph.kcache, tab[e].ph.vcache, pos, red);
       } else if (kind == K_SGU) {
         const SguArgs sa{tab[e].ph.ln_scale, reinterpret_cast<const float*>(tab[e].ph.wt), tab[e].ph.bias, tab[e].ph.kcache};
         sgu_phase(r, sa, pos, red);
