@@ -256,10 +256,16 @@ def run_decode_bench(args, cfgd):
         achieved = (wb + rest) / per_tok_s / 1e9
         per_step_b = secb / (genb / Bb)
         achieved_b = (wb + Bb * rest) / per_step_b / 1e9
-        roofline = dict(bound='hbm', achieved=achieved, peak=peaks['hbm'], unit='GB/s', frac=achieved / peaks['hbm'], traffic=None,
+        try:
+            dk = json.load(open(os.path.join(ROOT, 'profiles', 'r02_decode_kernel.json')))
+            traffic, traffic_b = dk['single']['dram_bytes_per_token'], dk['batched']['dram_bytes_per_step']
+        except Exception:
+            traffic = traffic_b = None
+        roofline = dict(bound='hbm', achieved=achieved, peak=peaks['hbm'], unit='GB/s', frac=achieved / peaks['hbm'], traffic=traffic,
+                        traffic_unit='DRAM bytes per token (ncu --set full of one 8-position launch, profiles/r02_ncu_decode_persistent.txt)',
                         kernel='decode_persistent_kernel<1, bf16> (one cooperative kernel for the whole generation)',
                         algorithmic_bytes_per_token=wb + rest, us_per_token=per_tok_s * 1e6, peak_source=peaks['source'],
-                        batched=dict(batch=Bb, tokens_per_sec=genb / secb, us_per_step=per_step_b * 1e6, achieved=achieved_b,
+                        batched=dict(batch=Bb, tokens_per_sec=genb / secb, us_per_step=per_step_b * 1e6, achieved=achieved_b, traffic=traffic_b,
                                      frac=achieved_b / peaks['hbm'], algorithmic_bytes_per_step=wb + Bb * rest))
         line = dict(metric='decode_tokens_per_sec', value=tps, unit='tokens/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=dev_s / args.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
