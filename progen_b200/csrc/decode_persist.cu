@@ -207,25 +207,72 @@ static __device__ __forceinline__ void load_wave(const Phase& ph, const Geo& g, 
   }
 }
 
-// everything of phase `ph` (pos filled in) that can be loaded before the barrier in front of it
-template <int BT, typename TW>
-static __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pre& pre) {
+// Single stream: what a warp / a finalizing thread needs of wave 0 of a phase, precomputed once per launch — the prefetch runs
+// between a barrier's arrive and wait on every warp, so its instruction count (divisions by runtime values, 64-bit offsets) is
+// phase time whenever it exceeds the barrier's own latency.
+struct __align__(16) UnitEnt { int off0, off1; short pl, ks; int kmax; };   // weight offsets of the unit's two rows (-1: no unit), columns left in its segment
+struct FinEnt { int r0, r1, d0, sel, rj; };                    // rows, store offset (sel: 0 out, 1 K cache, 2 V cache), rotary index
+static __device__ void build_unit_tables(const Phase& ph, UnitEnt* ut, FinEnt* ft, int u /* 0 .. WSEGS-1 */) {
   const Geo& g = ph.g;
-  load_wave<TW>(ph, g, 0, w);
-  if constexpr (BT == 1) {
-    const int t = threadIdx.x;
-    if (t < min(g.PW, g.np)) {                                  // this thread finalizes pair t of wave 0
-      const int pair = g.p_lo + t;
+  const int pw = min(g.PW, g.np);
+  {
+    const int pl = u / g.KS, ks = u - pl * g.KS;
+    UnitEnt e;
+    e.pl = (short)pl; e.ks = (short)ks; e.kmax = ph.K - ks * 256; e.off0 = e.off1 = -1;
+    if (pl < pw && e.kmax > 0) {
+      const int pair = g.p_lo + pl;
       const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
-      pre.b0 = ph.bias ? ph.bias[r0] : 0.f;
-      pre.b1 = ph.bias ? ph.bias[r1] : 0.f;
-      pre.d0 = ph.out + r0; pre.d1 = ph.out + r1;
-      if (ph.epi == EP_RESIDUAL) { pre.o0 = __ldcg(ph.out + r0); pre.o1 = __ldcg(ph.out + r1); }
+      e.off0 = r0 * ph.K + ks * 256; e.off1 = r1 * ph.K + ks * 256;
+    }
+    ut[u] = e;
+  }
+  {
+    FinEnt f{0, 0, 0, 0, 0};
+    if (u < pw) {
+      const int pair = g.p_lo + u;
+      f.r0 = ph.epi == EP_GLU ? pair : 2 * pair; f.r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+      f.d0 = f.r0;
       if (ph.epi == EP_ROTARY_CACHE) {
-        const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
-        pre.sn = ph.rot_sin[ph.pos * hd + j]; pre.cs = ph.rot_cos[ph.pos * hd + j];
-        const int sec = r0 / ph.inner, c = r0 % ph.inner;
-        pre.d0 = sec == 0 ? ph.out + c : (sec == 1 ? ph.kcache : ph.vcache) + ((long long)(c / ph.dim_head) * ph.n + ph.pos) * ph.dim_head + c % ph.dim_head;
+        const int sec = f.r0 / ph.inner, c = f.r0 % ph.inner;
+        f.rj = (f.r0 % ph.dim_head) >> 1;
+        f.sel = sec;
+        f.d0 = sec == 0 ? c : (c / ph.dim_head) * ph.n * ph.dim_head + c % ph.dim_head;
+      }
+    }
+    ft[u] = f;
+  }
+}
+
+// everything of phase `ph` (pos filled in) that can be loaded before the barrier in front of it.  ut / ft: this phase's
+// precomputed tables (single stream), or null
+template <int BT, typename TW>
+static __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>& w, Pre& pre, const UnitEnt* ut, const FinEnt* ft) {
+  const Geo& g = ph.g;
+  if constexpr (BT == 1) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const TW* W = reinterpret_cast<const TW*>(ph.wt);
+#pragma unroll
+    for (int i = 0; i < MAXSEG; ++i) {
+      const UnitEnt u = ut[warp + WPB * i];
+      w.pl[i] = u.pl; w.ks[i] = u.ks;
+      if (u.off0 >= 0 && lane * 8 < u.kmax) {
+        w8_load<TW>(w.a[i], W + u.off0 + lane * 8);
+        w8_load<TW>(w.c[i], W + u.off1 + lane * 8);
+      } else {
+        w8_zero<TW>(w.a[i]);
+        w8_zero<TW>(w.c[i]);
+      }
+    }
+    if (t < min(g.PW, g.np)) {                                  // this thread finalizes pair t of wave 0
+      const FinEnt f = ft[t];
+      pre.b0 = ph.bias ? ph.bias[f.r0] : 0.f;
+      pre.b1 = ph.bias ? ph.bias[f.r1] : 0.f;
+      pre.d0 = ph.out + f.r0; pre.d1 = ph.out + f.r1;
+      if (ph.epi == EP_RESIDUAL) { pre.o0 = __ldcg(ph.out + f.r0); pre.o1 = __ldcg(ph.out + f.r1); }
+      if (ph.epi == EP_ROTARY_CACHE) {
+        const int hd = ph.dim_head >> 1;
+        pre.sn = ph.rot_sin[ph.pos * hd + f.rj]; pre.cs = ph.rot_cos[ph.pos * hd + f.rj];
+        pre.d0 = (f.sel == 0 ? ph.out : (f.sel == 1 ? ph.kcache : ph.vcache) + ph.pos * ph.dim_head) + f.d0;
         pre.d1 = pre.d0 + 1;
       }
     }
@@ -234,6 +281,8 @@ static __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>
       pre.sc = *reinterpret_cast<const float4*>(ph.ln_scale + k);
       if (ph.ln_prev && k < (ph.K >> 1)) pre.pv = __ldcg(reinterpret_cast<const float4*>(ph.ln_prev + (ph.pos & 1) * (ph.K >> 1) + k));
     }
+  } else {
+    load_wave<TW>(ph, g, 0, w);
   }
 }
 
@@ -1406,6 +1455,15 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
   constexpr bool MERGE_IN_ATT = BT > 1;
   const bool att_consumer = !MERGE_IN_ATT && r.inner <= 4 * TPB;
   build_phase_table(r, tab, att_consumer, sgu_splits(r));
+  UnitEnt* utab = reinterpret_cast<UnitEnt*>((reinterpret_cast<uintptr_t>(tab + nph) + 15) & ~(uintptr_t)15);   // [nph][WSEGS]   (single stream only)
+  FinEnt* ftab = reinterpret_cast<FinEnt*>(utab + (BT == 1 ? nph * WSEGS : 0));
+  if constexpr (BT == 1) {
+    for (int idx = threadIdx.x; idx < nph * WSEGS; idx += TPB) {
+      const int e = idx / WSEGS, u = idx % WSEGS;
+      if (tab[e].kind == K_GEMV) build_unit_tables(tab[e].ph, utab + e * WSEGS, ftab + e * WSEGS, u);
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < BT * TL::XP; i += TPB) xs[i] = 0.f;     // tails beyond K are multiplied by zero weights: keep them finite
   __syncthreads();
   unsigned int round = 0;
@@ -1435,7 +1493,7 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
       if (kind == K_GEMV) {
         Phase ph = tab[e].ph;
         ph.pos = pos;
-        if (!have) prefetch_phase<BT, TW>(ph, w, pre);
+        if (!have) prefetch_phase<BT, TW>(ph, w, pre, utab + e * WSEGS, ftab + e * WSEGS);
         prof_mark(pf, 0);
         gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf, sbar, sparity);
         prof_mark(pf, 3);
@@ -1456,7 +1514,7 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
       if (fetch_next) {
         Phase nx = tab[tab[e].next].ph;
         nx.pos = e == nph - 2 ? pos + 1 : pos;               // the head's successor is layer 0 of the next position
-        prefetch_phase<BT, TW>(nx, w, pre);
+        prefetch_phase<BT, TW>(nx, w, pre, utab + tab[e].next * WSEGS, ftab + tab[e].next * WSEGS);
         prof_mark(pf, 4);
       }
       grid_wait(r.grid_bar, round, pf, t0);
@@ -1477,7 +1535,8 @@ int launch_run(const progen_decode_run_t& r, cudaStream_t s) {
   using TL = typename IM::template Tile<BT, sizeof(TW) == 2>;
   constexpr int TPB = threads_for(BT);
   static_assert((BT * TL::XP) % 4 == 0 && TL::PART % 4 == 0 && TL::WSM % 4 == 0, "the scratch regions must stay 16-byte aligned");
-  const size_t smem = IM::template decode_smem_floats<BT, sizeof(TW) == 2>() * sizeof(float) + (size_t)IM::num_phases(r.depth) * sizeof(typename IM::PhaseEnt);
+  const size_t smem = IM::template decode_smem_floats<BT, sizeof(TW) == 2>() * sizeof(float) + (size_t)IM::num_phases(r.depth) *
+                          (sizeof(typename IM::PhaseEnt) + (BT == 1 ? WSEGS * (sizeof(typename IM::UnitEnt) + sizeof(typename IM::FinEnt)) : 0)) + 16;
   PG_CHECK_ARG(smem <= 227 * 1024);
   auto kern = decode_persistent_kernel<BT, TW>;
   static size_t set_for = 0;
