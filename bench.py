@@ -271,7 +271,7 @@ def run_decode_bench(args, cfgd):
                     ms_per_step=dev_s / args.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f32' if args.fp32 else 'bf16', data='synthetic',
                     config=dict(workload=cfgd['name'], global_batch=world, seq_len=n, parallelism=f'replicas x{world}',
-                                l2='weights (103 MB bf16) fit the 126 MB L2; every position still streams them from L2/HBM once',
+                                l2='103 MB of bf16 weights + K/V do not stay in the 126 MB L2 between positions: ncu measures 125 MB of DRAM reads per token, the algorithmic 122 MB',
                                 step='one generation of %d tokens' % (gen_tokens // args.steps)),
                     e2e=dict(value=tps_e2e, unit='tokens/s', h2d_bytes_per_step=int(n * 4 + 4), d2h_bytes_per_step=int(n * 4),
                              ms_per_step=wall_s / args.steps * 1e3),
