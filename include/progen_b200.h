@@ -200,9 +200,10 @@ int progen_decode_step(const progen_decode_t* model, int do_sample, void* stream
  * pos0 .. pos0 + nsteps - 1 of B sequences in lock step (reference utils.py:106-135 per sequence; sample.py:66-71).
  * `layers` is a DEVICE array of `depth` progen_decode_layer_t whose cache / state pointers are batch-major:
  * kcache, vcache [B, heads, n, dim_head] (a head's keys are contiguous: the windowed read streams); shift1, shift2 [B, 2, d/2];
- * gn_hist [B, n, hid/2].  Sequence b keeps its prime before
- * start[b]: position p+1 is sampled (seq[b][p+1] += id, quirk Q5) iff p+1 >= start[b].  grid_bar (one uint32) and att_count
- * ([B * heads] int32) must be zero on entry.  B <= 64. */
+ * gn_hist [B, n, hid/2].  Sequence b keeps its prime before start[b]: position p+1 is sampled (seq[b][p+1] += id, quirk Q5)
+ * iff p+1 >= start[b].  grid_bar (one uint32) must be zero on entry; att_count ([B * heads] int32) is reserved (the attention
+ * merges no longer use a global counter).  Limits: B <= 64, dim_head a power of two in [8, 64], window <= 512, V <= 512,
+ * feature widths <= 8192. */
 typedef struct progen_decode_run_t {
   int32_t n, d, heads, dim_head, inner, window, hid, V, depth, wdtype, shift_tokens, top_k;
   int32_t B, pos0, nsteps, _pad;
@@ -221,7 +222,7 @@ typedef struct progen_decode_run_t {
   float* q;                    /* [B, inner] */
   float* att;                  /* [B, inner] */
   float* att_part;             /* [B, heads, ceil(2*window/32), dim_head + 4] partial (max, sum, -, -, out) per 32-key slice */
-  int32_t* att_count;          /* [B, heads] */
+  int32_t* att_count;          /* [B, heads] reserved (non-null) */
   float* u;                    /* [B, hid] */
   float* sg;                   /* [8, B, hid/2] partial spatial gates (up to 8 splits of the history range) */
   float* pj;                   /* [B, hid/2] */

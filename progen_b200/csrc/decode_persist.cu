@@ -1558,8 +1558,8 @@ int launch_run(const progen_decode_run_t& r, cudaStream_t s) {
 
 extern "C" {
 
-// Consume positions pos0 .. pos0 + nsteps - 1 of all B sequences in ONE kernel.  `grid_bar` and `att_count` must be zero on entry
-// (the kernel leaves att_count zero; the caller re-zeroes grid_bar before the next launch).
+// Consume positions pos0 .. pos0 + nsteps - 1 of all B sequences in ONE kernel.  `grid_bar` must be zero on entry (the caller
+// re-zeroes it before the next launch).
 int progen_decode_run(const progen_decode_run_t* r, void* stream) {
   PG_CHECK_ARG(r != nullptr && r->layers != nullptr && r->depth > 0 && r->B >= 1 && r->B <= 64 && r->nsteps >= 0);
   PG_CHECK_ARG(r->d % 8 == 0 && r->inner % 8 == 0 && r->hid % 256 == 0 && r->V % 2 == 0 && r->V <= 512);
