@@ -819,13 +819,15 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
                 split3_bf16x2(v2.x, v2.y, a1[2], a2[2], a3[2]);
                 split3_bf16x2(v3.x, v3.y, a1[3], a2[3], a3[3]);
               }
-              const __nv_bfloat16* wk = wb + gr * WKP + k0 + kb + gc;
+              const __nv_bfloat16* wk = wb + k0 + kb + gc;
               uint32_t fb0[NTC], fb1[NTC];
 #pragma unroll
               for (int nt = 0; nt < NTC; ++nt) {
-                const int nn = nt < NT ? nt : 0;               // (NT <= NTC; clamped: unconditional loads inside the staged rows)
-                fb0[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP);
-                fb1[nt] = *reinterpret_cast<const uint32_t*>(wk + nn * 8 * WKP + 8);
+                // row of the staged slice this lane's fragment column comes from; clamped to the 2 * PW rows that exist (wide K:
+                // PW < 4, i.e. fewer than 8 rows — columns past them belong to no pair and are dropped by the epilogue)
+                const int row = min((nt < NT ? nt : 0) * 8 + gr, 2 * g.PW - 1);
+                fb0[nt] = *reinterpret_cast<const uint32_t*>(wk + row * WKP);
+                fb1[nt] = *reinterpret_cast<const uint32_t*>(wk + row * WKP + 8);
               }
               // term-major, smallest terms first: consecutive MMAs hit different accumulators
 #pragma unroll

@@ -125,6 +125,33 @@ def test_batched_logits_match_oracle_forward(B, wdt):
         assert np.abs(got[b, :n - 1] - ref[:n - 1]).max() < 3e-5 * max(1.0, np.abs(ref).max()), b
 
 
+@pytest.mark.parametrize('B,wdt', [(1, 'f32'), (1, 'bf16'), (5, 'f32'), (12, 'bf16'), (40, 'bf16'), (20, 'f32')])
+def test_decode_wide_model_multiwave(B, wdt):
+    """d = 1024 (config-3 width): a CTA's share of a GEMV phase no longer fits one wave of weight units (QKV 2 waves, FF-in 4),
+    K = 1024 / 4096 inputs are staged in several chunks for B > 8, LayerNorm takes the two-pass path there.  Logits of every
+    position against the oracle's forward (bf16 weights: oracle on the rounded weights)."""
+    import torch
+    from progen_b200.decode import BatchDecoder
+    from oracle import progen_ref as O
+    cfg = O.make_config(num_tokens=256, dim=1024, seq_len=48, depth=2, window_size=16, global_mlp_depth=1, heads=16, dim_head=64)
+    params = O.randomize_params(O.init_params(cfg, 11), 12)
+    rng = np.random.default_rng(B)
+    primes = [rng.integers(1, 256, int(rng.integers(1, 6))).astype(np.int64) for _ in range(B)]
+    dt = torch.bfloat16 if wdt == 'bf16' else torch.float32
+    dec = BatchDecoder(cfg, params, batch=B, weights_dtype=dt, keep_logits=True)
+    dec.sample(primes if B > 1 else primes[0], top_k=25, add_bos=True, greedy=True)
+    seqs = dec.seq.cpu().numpy().astype(np.int64)
+    got = dec.logits_all.cpu().numpy()
+    ref_params = params
+    if wdt == 'bf16':
+        rnd = lambda a: torch.tensor(np.asarray(a, np.float32)).bfloat16().float().numpy()
+        ref_params = {k: {kk: (rnd(vv) if kk == 'w' else vv) for kk, vv in v.items()} for k, v in params.items()}
+    n = cfg['seq_len']
+    for b in sorted({0, B // 2, B - 1}):
+        ref = O.forward(ref_params, np.clip(seqs[b], 0, 255), cfg)
+        assert np.abs(got[b, :n - 1] - ref[:n - 1]).max() < 5e-5 * max(1.0, np.abs(ref).max()), b
+
+
 @pytest.mark.parametrize('B', [12, 40])
 def test_batched_tensor_pipe_path_at_model_width_512(B):
     """config-1 width (d = 512, K = 512 / 2048 phases: bulk-copied LayerNorm rows, multi-chunk FF-out, 1-4 n-tiles per CTA) with
