@@ -250,21 +250,38 @@ static __device__ __forceinline__ void prefetch_phase(const Phase& ph, WRegs<TW>
   const Geo& g = ph.g;
   if constexpr (BT == 1) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const TW* W = reinterpret_cast<const TW*>(ph.wt);
+    if (ut != nullptr) {
+      const TW* W = reinterpret_cast<const TW*>(ph.wt);
 #pragma unroll
-    for (int i = 0; i < MAXSEG; ++i) {
-      const UnitEnt u = ut[warp + WPB * i];
-      w.pl[i] = u.pl; w.ks[i] = u.ks;
-      if (u.off0 >= 0 && lane * 8 < u.kmax) {
-        w8_load<TW>(w.a[i], W + u.off0 + lane * 8);
-        w8_load<TW>(w.c[i], W + u.off1 + lane * 8);
-      } else {
-        w8_zero<TW>(w.a[i]);
-        w8_zero<TW>(w.c[i]);
+      for (int i = 0; i < MAXSEG; ++i) {
+        const UnitEnt u = ut[warp + WPB * i];
+        w.pl[i] = u.pl; w.ks[i] = u.ks;
+        if (u.off0 >= 0 && lane * 8 < u.kmax) {
+          w8_load<TW>(w.a[i], W + u.off0 + lane * 8);
+          w8_load<TW>(w.c[i], W + u.off1 + lane * 8);
+        } else {
+          w8_zero<TW>(w.a[i]);
+          w8_zero<TW>(w.c[i]);
+        }
       }
+    } else {
+      load_wave<TW>(ph, g, 0, w);                                // (deep models: the per-launch tables do not fit shared memory)
     }
     if (t < min(g.PW, g.np)) {                                  // this thread finalizes pair t of wave 0
-      const FinEnt f = ft[t];
+      FinEnt f;
+      if (ft != nullptr) {
+        f = ft[t];
+      } else {
+        const int pair = g.p_lo + t;
+        f.r0 = ph.epi == EP_GLU ? pair : 2 * pair; f.r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+        f.d0 = f.r0; f.sel = 0; f.rj = 0;
+        if (ph.epi == EP_ROTARY_CACHE) {
+          const int sec = f.r0 / ph.inner, c = f.r0 % ph.inner;
+          f.rj = (f.r0 % ph.dim_head) >> 1;
+          f.sel = sec;
+          f.d0 = sec == 0 ? c : (c / ph.dim_head) * ph.n * ph.dim_head + c % ph.dim_head;
+        }
+      }
       pre.b0 = ph.bias ? ph.bias[f.r0] : 0.f;
       pre.b1 = ph.bias ? ph.bias[f.r1] : 0.f;
       pre.d0 = ph.out + f.r0; pre.d1 = ph.out + f.r1;
@@ -1434,6 +1451,11 @@ static __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt*
   __syncthreads();
 }
 
+static constexpr size_t MAX_SMEM = 227 * 1024;
+// dynamic shared memory of a launch: the tile regions, the phase table and (single stream, when they fit) the unit tables
+template <int BT, bool TCW> static __host__ __device__ size_t decode_smem_bytes(int depth, bool with_unit_tables) {
+  return decode_smem_floats<BT, TCW>() * sizeof(float) + (size_t)num_phases(depth) * (sizeof(PhaseEnt) + (with_unit_tables ? WSEGS * (sizeof(UnitEnt) + sizeof(FinEnt)) : 0)) + 16;
+}
 template <int BT, bool TCW> static constexpr size_t decode_smem_floats() {
   using TL = Tile<BT, TCW>;
   return (size_t)BT * TL::XP + TL::PART + TL::STATF + TL::WSM + WPB * 128 + 64;
@@ -1457,9 +1479,10 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
   constexpr bool MERGE_IN_ATT = BT > 1;
   const bool att_consumer = !MERGE_IN_ATT && r.inner <= 4 * TPB;
   build_phase_table(r, tab, att_consumer, sgu_splits(r));
+  const bool use_tabs = BT == 1 && decode_smem_bytes<BT, sizeof(TW) == 2>(r.depth, true) <= MAX_SMEM;
   UnitEnt* utab = reinterpret_cast<UnitEnt*>((reinterpret_cast<uintptr_t>(tab + nph) + 15) & ~(uintptr_t)15);   // [nph][WSEGS]   (single stream only)
-  FinEnt* ftab = reinterpret_cast<FinEnt*>(utab + (BT == 1 ? nph * WSEGS : 0));
-  if constexpr (BT == 1) {
+  FinEnt* ftab = reinterpret_cast<FinEnt*>(utab + (use_tabs ? nph * WSEGS : 0));
+  if (use_tabs) {
     for (int idx = threadIdx.x; idx < nph * WSEGS; idx += TPB) {
       const int e = idx / WSEGS, u = idx % WSEGS;
       if (tab[e].kind == K_GEMV) build_unit_tables(tab[e].ph, utab + e * WSEGS, ftab + e * WSEGS, u);
@@ -1495,7 +1518,7 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
       if (kind == K_GEMV) {
         Phase ph = tab[e].ph;
         ph.pos = pos;
-        if (!have) prefetch_phase<BT, TW>(ph, w, pre, utab + e * WSEGS, ftab + e * WSEGS);
+        if (!have) prefetch_phase<BT, TW>(ph, w, pre, use_tabs ? utab + e * WSEGS : nullptr, use_tabs ? ftab + e * WSEGS : nullptr);
         prof_mark(pf, 0);
         gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf, sbar, sparity);
         prof_mark(pf, 3);
@@ -1516,7 +1539,7 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
       if (fetch_next) {
         Phase nx = tab[tab[e].next].ph;
         nx.pos = e == nph - 2 ? pos + 1 : pos;               // the head's successor is layer 0 of the next position
-        prefetch_phase<BT, TW>(nx, w, pre, utab + tab[e].next * WSEGS, ftab + tab[e].next * WSEGS);
+        prefetch_phase<BT, TW>(nx, w, pre, use_tabs ? utab + tab[e].next * WSEGS : nullptr, use_tabs ? ftab + tab[e].next * WSEGS : nullptr);
         prof_mark(pf, 4);
       }
       grid_wait(r.grid_bar, round, pf, t0);
@@ -1537,9 +1560,9 @@ int launch_run(const progen_decode_run_t& r, cudaStream_t s) {
   using TL = typename IM::template Tile<BT, sizeof(TW) == 2>;
   constexpr int TPB = threads_for(BT);
   static_assert((BT * TL::XP) % 4 == 0 && TL::PART % 4 == 0 && TL::WSM % 4 == 0, "the scratch regions must stay 16-byte aligned");
-  const size_t smem = IM::template decode_smem_floats<BT, sizeof(TW) == 2>() * sizeof(float) + (size_t)IM::num_phases(r.depth) *
-                          (sizeof(typename IM::PhaseEnt) + (BT == 1 ? WSEGS * (sizeof(typename IM::UnitEnt) + sizeof(typename IM::FinEnt)) : 0)) + 16;
-  PG_CHECK_ARG(smem <= 227 * 1024);
+  size_t smem = IM::template decode_smem_bytes<BT, sizeof(TW) == 2>(r.depth, BT == 1);
+  if (smem > IM::MAX_SMEM) smem = IM::template decode_smem_bytes<BT, sizeof(TW) == 2>(r.depth, false);   // deep model: no unit tables
+  PG_CHECK_ARG(smem <= IM::MAX_SMEM);                                  // (the phase table itself: depth * 7 + 2 entries)
   auto kern = decode_persistent_kernel<BT, TW>;
   static size_t set_for = 0;
   if (set_for < smem) {

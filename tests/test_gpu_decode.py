@@ -152,6 +152,32 @@ def test_decode_wide_model_multiwave(B, wdt):
         assert np.abs(got[b, :n - 1] - ref[:n - 1]).max() < 5e-5 * max(1.0, np.abs(ref).max()), b
 
 
+@pytest.mark.parametrize('B,wdt,depth,window', [(1, 'f32', 26, 16), (1, 'bf16', 4, 512), (12, 'bf16', 4, 512), (3, 'f32', 26, 16)])
+def test_decode_deep_models_and_wide_windows(B, wdt, depth, window):
+    """depth 26: the single-stream unit tables no longer fit shared memory (the kernel computes the offsets instead);
+    window 512 at seq_len 1024: up to 32 key slices of 32 (single stream) / 64 of 16 (batched) per (sequence, head)"""
+    import torch
+    from progen_b200.decode import BatchDecoder
+    from oracle import progen_ref as O
+    n = 1024 if window == 512 else 48
+    cfg = O.make_config(num_tokens=256, dim=64, seq_len=n, depth=depth, window_size=window, global_mlp_depth=2, heads=2, dim_head=32)
+    params = O.randomize_params(O.init_params(cfg, 21), 22)
+    rng = np.random.default_rng(B + depth)
+    primes = [rng.integers(1, 256, int(rng.integers(1, 6))).astype(np.int64) for _ in range(B)]
+    dt = torch.bfloat16 if wdt == 'bf16' else torch.float32
+    dec = BatchDecoder(cfg, params, batch=B, weights_dtype=dt, keep_logits=True)
+    dec.sample(primes if B > 1 else primes[0], top_k=25, add_bos=True, greedy=True)
+    seqs = dec.seq.cpu().numpy().astype(np.int64)
+    got = dec.logits_all.cpu().numpy()
+    ref_params = params
+    if wdt == 'bf16':
+        rnd = lambda a: torch.tensor(np.asarray(a, np.float32)).bfloat16().float().numpy()
+        ref_params = {k: {kk: (rnd(vv) if kk == 'w' else vv) for kk, vv in v.items()} for k, v in params.items()}
+    for b in sorted({0, B - 1}):
+        ref = O.forward(ref_params, np.clip(seqs[b], 0, 255), cfg)
+        assert np.abs(got[b, :n - 1] - ref[:n - 1]).max() < 1e-4 * max(1.0, np.abs(ref).max()), b
+
+
 @pytest.mark.parametrize('B', [12, 40])
 def test_batched_tensor_pipe_path_at_model_width_512(B):
     """config-1 width (d = 512, K = 512 / 2048 phases: bulk-copied LayerNorm rows, multi-chunk FF-out, 1-4 n-tiles per CTA) with
