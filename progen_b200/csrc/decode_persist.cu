@@ -158,6 +158,7 @@ struct Phase {
   float* ln_prev;          // [B][2][K/2] token-shift state (read [pos&1], write [(pos+1)&1]); null: no shift
   const float* aux;        // PRO_ATT: att_part; PRO_SGU: partial gates [nsplit][B][K]
   int window, nsplit;
+  long long aux_stride;    // PRO_SGU: elements between two splits' partial gates (total sequences x K)
   // rotary / cache epilogue
   float* kcache; float* vcache; int inner, dim_head, n;
   const float* rot_sin; const float* rot_cos;
@@ -365,7 +366,7 @@ static __device__ __forceinline__ float4 merge_att(const Phase& ph, int k) {
 // prefetch_phase loaded for THIS phase (the caller ran it before the previous grid barrier, or just now).
 template <int BT, typename TW>
 static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float* xs, float* part, float* stat, float* wsm, WRegs<TW>& w, const Pre& pre, const Prof& pf,
-                                           uint32_t sbar, uint32_t& sparity) {
+                                           uint32_t sbar, uint32_t& sparity, bool reload_w0 = false) {
   using TL = Tile<BT, sizeof(TW) == 2>;
   constexpr int KCB = TL::KCB, XP = TL::XP, BTP = TL::BTP;
   constexpr bool LANEB = TL::LANEB, TC = TL::TC;
@@ -388,7 +389,7 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
 #pragma unroll
       for (int s = 0; s < MAXSPLIT; ++s) {
         if (s < ph.nsplit) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(ph.aux + (long long)s * ph.K + k));
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ph.aux + s * ph.aux_stride + k));
           gsum.x += v.x; gsum.y += v.y; gsum.z += v.z; gsum.w += v.w;
         }
       }
@@ -639,7 +640,7 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
         const int b = idx / (kn >> 2), k = (idx % (kn >> 2)) * 4;
         float4 gsum = gq[u];
         for (int sp = 1; sp < ph.nsplit; ++sp) {
-          const float4 q = __ldcg(reinterpret_cast<const float4*>(ph.aux + ((long long)sp * B + b) * ph.K + k0 + k));
+          const float4 q = __ldcg(reinterpret_cast<const float4*>(ph.aux + sp * ph.aux_stride + (long long)b * ph.K + k0 + k));
           gsum.x += q.x; gsum.y += q.y; gsum.z += q.z; gsum.w += q.w;
         }
         *reinterpret_cast<float4*>(xs + b * XP + xs_off<BT>(k)) = make_float4(t[u].x * gsum.x, t[u].y * gsum.y, t[u].z * gsum.z, t[u].w * gsum.w);
@@ -691,7 +692,7 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
   if (!staged && nchunks == 1) { stage(0); __syncthreads(); }
   prof_mark(pf, 1);
   for (int wave = 0; wave < g.nwaves; ++wave) {
-    if (wave > 0) load_wave<TW>(ph, g, wave, w);
+    if (wave > 0 || (reload_w0 && g.nwaves > 1)) load_wave<TW>(ph, g, wave, w);   // (a later sub-batch of a multi-wave phase: `w` holds the last wave)
     const int pbase = wave * g.PW;
     const int pw = min(g.PW, g.np - pbase);
     if constexpr (!LANEB) {
@@ -1428,7 +1429,7 @@ static __device__ void build_phase_table(const progen_decode_run_t& r, PhaseEnt*
       e[4].kind = K_SGU; e[4].ph = ph;
       ph = Phase{};
       ph.wt = L.sgu_proj_t; ph.bias = L.sgu_proj_b; ph.xin = r.u; ph.ldx = hid; ph.out = r.pj; ph.ldo = hid / 2; ph.N = hid / 2; ph.K = hid / 2;
-      ph.epi = EP_BIAS; ph.pro = PRO_SGU; ph.aux = r.sg; ph.nsplit = nsplit;
+      ph.epi = EP_BIAS; ph.pro = PRO_SGU; ph.aux = r.sg; ph.nsplit = nsplit; ph.aux_stride = (long long)r.B * (hid / 2);
       ph.g = make_geo(ph);
       e[5].kind = K_GEMV; e[5].ph = ph; e[5].next = li * 7 + 6;
       last = r.pj; last_k = hid / 2;
@@ -1520,7 +1521,22 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
         ph.pos = pos;
         if (!have) prefetch_phase<BT, TW>(ph, w, pre, use_tabs ? utab + e * WSEGS : nullptr, use_tabs ? ftab + e * WSEGS : nullptr);
         prof_mark(pf, 0);
-        gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf, sbar, sparity);
+        if (B <= BT) {
+          gemv_phase<BT, TW>(ph, B, xs, part, stat, wsm, w, pre, pf, sbar, sparity);
+        } else {
+          // more sequences than the batch tile: sub-batches of BT sequences run through the phase one after the other with
+          // the same weights (per warp, 32 sequences cost 4 LayerNorm rows and 8 k-steps; a 64-wide tile costs twice that
+          // in series — measured: 32 sequences 0.73 ms per step, a 64-wide tile 1.31 ms)
+          for (int b0 = 0; b0 < B; b0 += BT) {
+            Phase ps = ph;
+            if (ps.xin) ps.xin += (long long)b0 * ps.ldx;
+            ps.out += (long long)b0 * ps.ldo;
+            if (ps.ln_prev) ps.ln_prev += (long long)b0 * ps.K;
+            if (ps.kcache) { ps.kcache += (long long)b0 * ps.n * ps.inner; ps.vcache += (long long)b0 * ps.n * ps.inner; }
+            if (ps.pro == PRO_SGU) ps.aux += (long long)b0 * ps.K;
+            gemv_phase<BT, TW>(ps, min(BT, B - b0), xs, part, stat, wsm, w, pre, pf, sbar, sparity, b0 > 0);
+          }
+        }
         prof_mark(pf, 3);
         have = fetch_next = !(e == nph - 2 && step + 1 == r.nsteps);
       } else if (kind == K_ATT) {
@@ -1598,7 +1614,9 @@ int progen_decode_run(const progen_decode_run_t* r, void* stream) {
   const bool bf = r->wdtype == PG_BF16;
   if (r->B == 1) return bf ? launch_run<1, bf16>(*r, s) : launch_run<1, float>(*r, s);
   if (r->B <= 8) return bf ? launch_run<8, bf16>(*r, s) : launch_run<8, float>(*r, s);
-  if (r->B <= 32) return bf ? launch_run<32, bf16>(*r, s) : launch_run<32, float>(*r, s);
+  // 9 .. 64 sequences: the 32-sequence tile, twice per phase above 32 (PROGEN_DECODE_TILE64=1: one 64-wide tile, kept for A/B)
+  static const bool tile64 = [] { const char* e = getenv("PROGEN_DECODE_TILE64"); return e && atoi(e) != 0; }();
+  if (r->B <= 32 || !tile64) return bf ? launch_run<32, bf16>(*r, s) : launch_run<32, float>(*r, s);
   return bf ? launch_run<64, bf16>(*r, s) : launch_run<64, float>(*r, s);
 }
 
