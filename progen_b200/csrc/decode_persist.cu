@@ -375,6 +375,25 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
   const int nchunks = (ph.K + KCB - 1) / KCB;
   const int half = ph.K >> 1;
   bool staged = false;
+  bool wsm_ready = false;
+  if constexpr (TC) {
+    // tensor pipe: wave 0's weights (prefetched registers) go to shared memory first — nothing of it depends on the
+    // activations, so it overlaps their copy instead of following the LayerNorm (the previous phase's / pass's readers of wsm
+    // are behind a CTA barrier already)
+    if (!(reload_w0 && g.nwaves > 1)) {
+      const int WKP = g.KS * 256 + 8;
+      __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(wsm);
+#pragma unroll
+      for (int i = 0; i < MAXSEG; ++i) {
+        const int pl = w.pl[i], ks = w.ks[i];
+        if (pl >= g.PW) continue;
+        __nv_bfloat16* d0 = wb + (2 * pl) * WKP + ks * 256 + lane * 8;
+        *reinterpret_cast<uint4*>(d0) = w.a[i].q[0];
+        *reinterpret_cast<uint4*>(d0 + WKP) = w.c[i].q[0];
+      }
+      wsm_ready = true;
+    }
+  }
   if (BT == 1 && ph.K <= 4 * TPB) {
     // single sequence, one float4 per thread: LN statistics, scale, token shift and the staging in one pass
     const int k = threadIdx.x * 4;
@@ -798,14 +817,16 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
         constexpr int NMT = TL::NMT, NKH = TL::NKH, NTMAX = 2 * WSEGS / 8;
         const int WK = g.KS * 256, WKP = WK + 8;               // +8 bf16: the 8 rows of a B fragment land in distinct banks
         __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(wsm);
-        __syncthreads();                                       // the previous wave's / phase's readers of wsm are done
+        if (!(wave == 0 && wsm_ready)) {                       // (wave 0 was written at the top of the phase, under the activation copies)
+          __syncthreads();                                     // the previous wave's readers of wsm are done
 #pragma unroll
-        for (int i = 0; i < MAXSEG; ++i) {
-          const int pl = w.pl[i], ks = w.ks[i];
-          if (pl >= g.PW) continue;
-          __nv_bfloat16* d0 = wb + (2 * pl) * WKP + ks * 256 + lane * 8;
-          *reinterpret_cast<uint4*>(d0) = w.a[i].q[0];
-          *reinterpret_cast<uint4*>(d0 + WKP) = w.c[i].q[0];
+          for (int i = 0; i < MAXSEG; ++i) {
+            const int pl = w.pl[i], ks = w.ks[i];
+            if (pl >= g.PW) continue;
+            __nv_bfloat16* d0 = wb + (2 * pl) * WKP + ks * 256 + lane * 8;
+            *reinterpret_cast<uint4*>(d0) = w.a[i].q[0];
+            *reinterpret_cast<uint4*>(d0 + WKP) = w.c[i].q[0];
+          }
         }
         // (2) warp = (m-tile of 16 sequences, K split): C[16 x 8 per n-tile] += A[16 x 16](x, three bf16 terms) B[16 x 8](weights)
         const int mt = warp % NMT, kh = warp / NMT;
@@ -814,6 +835,34 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
         float acc[NTMAX][4];
 #pragma unroll
         for (int nt = 0; nt < NTMAX; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+        // epilogue operands of n-tiles n0, n0 + 1 for this lane's two sequences (b0, b0 + 8) and pair 4 nt + (lane & 3)
+        const int b0 = mt * 16 + gr;
+        auto load_ops = [&](int n0, float (&bia)[2][2], float (&old)[2][4], float (&rot)[2][2]) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int nt = n0 + u;
+            const int pl = nt * 4 + (lane & 3);
+            const bool v = nt < NT && pl < pw;
+            const int pair = g.p_lo + pbase + (v ? pl : 0);
+            const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
+            bia[u][0] = ph.bias ? ph.bias[r0] : 0.f;
+            bia[u][1] = ph.bias ? ph.bias[r1] : 0.f;
+            old[u][0] = old[u][1] = old[u][2] = old[u][3] = 0.f;
+            if (ph.epi == EP_RESIDUAL) {
+              const float* o0 = ph.out + (long long)(b0 < B ? b0 : 0) * ph.ldo;
+              const float* o1 = ph.out + (long long)(b0 + 8 < B ? b0 + 8 : 0) * ph.ldo;
+              old[u][0] = __ldcg(o0 + r0); old[u][1] = __ldcg(o0 + r1);
+              old[u][2] = __ldcg(o1 + r0); old[u][3] = __ldcg(o1 + r1);
+            }
+            rot[u][0] = rot[u][1] = 0.f;
+            if (ph.epi == EP_ROTARY_CACHE) {
+              const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
+              rot[u][0] = ph.rot_sin[ph.pos * hd + j]; rot[u][1] = ph.rot_cos[ph.pos * hd + j];
+            }
+          }
+        };
+        float bia0[2][2], old0[2][4], rot0[2][2];
+        load_ops(0, bia0, old0, rot0);                         // in flight under the MMA loop (every warp: kh is only known to be 0 later)
         for (int kc = 0; kc < nchunks; ++kc) {
           __syncthreads();                                     // wsm written (kc == 0) / the previous chunk's xs readers done
           if (kc == 0) prof_mark(pf, 5);
@@ -888,33 +937,19 @@ static __device__ __forceinline__ void gemv_phase(const Phase& ph, int B, float*
         prof_mark(pf, 2);
         if (kh == 0) {
           // two n-tiles at a time: every operand of their epilogues first (bias, old residual values, rotary entries:
-          // independent loads), then the math and the stores
-          const int b0 = mt * 16 + gr;
+          // independent loads; those of the first two n-tiles were requested before the MMA loop), then the math and the stores
 #pragma unroll
           for (int n0 = 0; n0 < NTMAX; n0 += 2) {
             if (n0 >= NT) continue;                            // (no break: the loop must unroll, acc[] is indexed statically)
             float bia[2][2], old[2][4], rot[2][2];
+            if (n0 == 0) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int nt = n0 + u;
-              const int pl = nt * 4 + (lane & 3);
-              const bool v = nt < NT && pl < pw;
-              const int pair = g.p_lo + pbase + (v ? pl : 0);
-              const int r0 = ph.epi == EP_GLU ? pair : 2 * pair, r1 = ph.epi == EP_GLU ? pair + ph.N : 2 * pair + 1;
-              bia[u][0] = ph.bias ? ph.bias[r0] : 0.f;
-              bia[u][1] = ph.bias ? ph.bias[r1] : 0.f;
-              old[u][0] = old[u][1] = old[u][2] = old[u][3] = 0.f;
-              if (ph.epi == EP_RESIDUAL) {
-                const float* o0 = ph.out + (long long)(b0 < B ? b0 : 0) * ph.ldo;
-                const float* o1 = ph.out + (long long)(b0 + 8 < B ? b0 + 8 : 0) * ph.ldo;
-                old[u][0] = __ldcg(o0 + r0); old[u][1] = __ldcg(o0 + r1);
-                old[u][2] = __ldcg(o1 + r0); old[u][3] = __ldcg(o1 + r1);
+              for (int u = 0; u < 2; ++u) {
+                bia[u][0] = bia0[u][0]; bia[u][1] = bia0[u][1]; rot[u][0] = rot0[u][0]; rot[u][1] = rot0[u][1];
+                old[u][0] = old0[u][0]; old[u][1] = old0[u][1]; old[u][2] = old0[u][2]; old[u][3] = old0[u][3];
               }
-              rot[u][0] = rot[u][1] = 0.f;
-              if (ph.epi == EP_ROTARY_CACHE) {
-                const int hd = ph.dim_head >> 1, j = (r0 % ph.dim_head) >> 1;
-                rot[u][0] = ph.rot_sin[ph.pos * hd + j]; rot[u][1] = ph.rot_cos[ph.pos * hd + j];
-              }
+            } else {
+              load_ops(n0, bia, old, rot);
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
