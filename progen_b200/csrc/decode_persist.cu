@@ -7,16 +7,19 @@
 // (one atomic + one acquire poll per CTA), and the token loop, the sampler (top-k filter that keeps k-1 and zeroes the
 // rest, Gumbel-max, `seq[pos+1] += id` — quirks Q5/Q6) and the position counter stay on the device: no host round trip.
 //
-// A position is ~65 dependent phases, so single-stream speed is LATENCY: every global load that does not depend on the
-// previous phase's output (the CTA's slice of the weights, biases, LN scales, rotary entries, the residual it will add to)
-// is issued BEFORE the grid barrier that precedes the phase and waited for after it; what is left on the critical path is
-// one L2 round trip for the activations, two block reductions (LN), the FMAs and the barrier itself.
+// A position is ~65 dependent phases, so single-stream speed is LATENCY: a barrier is arrive -> prefetch -> wait, and between
+// the atomic and the poll every warp requests what does not depend on the other CTAs' output of the phase: its slice of the
+// NEXT GEMV phase's weights (registers), biases, LN scales, rotary entries, the residual values it will add to (offsets and
+// rows come from per-launch tables).  What is left on the critical path is one L2 round trip for the activations, two block
+// reductions (LN), the FMAs, a 9-shuffle reduction and the barrier itself.
 //
 // BATCH: `B` sequences advance in lock step ([B, 1] rows per step) and the step streams the weights ONCE for all of them.
 // B <= 8: a lane holds 8 weights of two rows and multiplies them with every staged activation row (reduction over lanes).
-// B > 8: lane = sequence — the CTA's weight slice is staged in shared memory as fp32 and read with broadcast loads, each
-// lane keeps 32 activations of its sequence in registers and accumulates its warp's rows, so the FMA pipe, not
-// shared-memory bandwidth, is the bound.  Sequence b samples position p+1 iff p+1 >= start[b] (its prime is kept before).
+// B > 8, bf16 weights: tensor pipe — the CTA's weight slice goes to shared memory as bf16, every fp32 activation is split into
+// three bf16 terms (8 + 8 + 8 mantissa bits) and mma.sync.m16n8k16 accumulates the exact products in fp32; activations arrive by
+// bulk copies, LayerNorm rows are normalised in shared memory.  B > 8, fp32 weights: lane = sequence, weights broadcast from
+// shared memory.  More than 32 sequences: the 32-sequence tile runs twice per phase on the same staged weights.
+// Sequence b samples position p+1 iff p+1 >= start[b] (its prime is kept before).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "../../include/progen_b200.h"
