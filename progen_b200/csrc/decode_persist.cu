@@ -1566,6 +1566,7 @@ static __device__ __forceinline__ void run(const progen_decode_run_t& r) {
           // the same weights (per warp, 32 sequences cost 4 LayerNorm rows and 8 k-steps; a 64-wide tile costs twice that
           // in series — measured: 32 sequences 0.73 ms per step, a 64-wide tile 1.31 ms)
           for (int b0 = 0; b0 < B; b0 += BT) {
+            if (b0 > 0) __syncthreads();                       // every warp is done reading the previous pass's staged rows
             Phase ps = ph;
             if (ps.xin) ps.xin += (long long)b0 * ps.ldx;
             ps.out += (long long)b0 * ps.ldo;
