@@ -51,3 +51,37 @@ def test_product_has_no_oracle_or_cpu_fallback():
         from progen_b200 import lib as L
         with pytest.raises(L.ProgenError):
             L.require_device()
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every ctypes mirror of a C-ABI struct has the size and the field offsets gcc gives the declaration in
+    include/progen_b200.h (a field added on one side only would shift every pointer after it)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from progen_b200 import lib as L
+    from progen_b200 import decode as D
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    pairs = [('progen_gemm_t', L.GemmDesc), ('progen_decode_layer_t', D.DecodeLayer), ('progen_decode_t', D.DecodeModel),
+             ('progen_decode_run_t', D.DecodeRun)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "progen_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    inc = os.path.join(ROOT, 'include')
+    subprocess.run(['gcc', '-std=c11', '-I', inc, str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    want = {}
+    for ln in out.strip().splitlines():
+        c, f, v = ln.split()
+        want[(c, f)] = int(v)
+    for cname, cls in pairs:
+        assert C.sizeof(cls) == want[(cname, 'size')], cname
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == want[(cname, fname)], (cname, fname)
